@@ -1,0 +1,140 @@
+/*
+ * scdrs_b200 -- C ABI of the B200 (sm_100a) scoring hot path of scDRS.
+ *
+ * The reference (martinjzhang/scDRS) is pure Python and has no FFI; the functions below are
+ * the native boundary its hot path would bind (the ctypes stub a maintainer would add is shown
+ * in INTEGRATION.md and is what scdrs_b200/_native.py uses).  Each entry point cites the
+ * reference code it replaces, paths relative to the reference root.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on failure, and
+ *     scdrs_last_error() then returns a thread-local message.  There is no CPU fallback.
+ *   - "host" pointers are ordinary host memory (pinned or pageable); "dev" pointers are device
+ *     memory on the context's GPU.  All work is enqueued on the context's stream; functions
+ *     that fill host outputs synchronise that stream before returning.
+ *   - matrices are row-major.  Column 0 of every (1 + n_ctrl)-column object is the trait gene
+ *     set, columns 1..n_ctrl are the control gene sets.
+ */
+#ifndef SCDRS_B200_H
+#define SCDRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scdrs_ctx scdrs_ctx;
+
+/* weight_opt of scdrs/method.py:366-371 */
+enum { SCDRS_WEIGHT_UNIFORM = 0, SCDRS_WEIGHT_VS = 1, SCDRS_WEIGHT_INV_STD = 2 };
+
+const char* scdrs_last_error(void);
+int scdrs_abi_version(void);
+
+/* ---- context: one per (GPU, expression matrix) ------------------------------------------ */
+int scdrs_ctx_create(int device, scdrs_ctx** out);
+int scdrs_ctx_destroy(scdrs_ctx* ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own */
+int scdrs_ctx_set_stream(scdrs_ctx* ctx, void* cuda_stream);
+int scdrs_ctx_sync(scdrs_ctx* ctx);
+/* number of kernel launches issued through this context since creation (bench bookkeeping) */
+int64_t scdrs_ctx_launch_count(scdrs_ctx* ctx);
+/* device time (ms) of the last scdrs_trait_raw scatter kernel / whole scdrs_score_trait call,
+ * measured with CUDA events on the context's stream; valid after a sync */
+int scdrs_ctx_last_timing(scdrs_ctx* ctx, float* spmm_ms, float* trait_ms);
+
+/* ---- resident inputs ---------------------------------------------------------------------
+ * adata.X as CSR (cells x genes): float32 values, int32 column ids, int64 row pointers.
+ * Replaces the CSC copy of scdrs/method.py:98-99.  _host copies H2D, _dev borrows pointers. */
+int scdrs_set_csr_host(scdrs_ctx* ctx, int64_t n_cell, int32_t n_gene, const int64_t* indptr,
+                       const int32_t* indices, const float* data);
+int scdrs_set_csr_dev(scdrs_ctx* ctx, int64_t n_cell, int32_t n_gene, const int64_t* dev_indptr,
+                      const int32_t* dev_indices, const float* dev_data);
+/* GENE_STATS["var"], GENE_STATS["var_tech"] (scdrs/method.py:369-371, 192-195); host, n_gene each */
+int scdrs_set_gene_stats(scdrs_ctx* ctx, const double* var, const double* var_tech);
+/* implicit covariate correction terms COV_MAT (n_cell x k), COV_BETA (n_gene x k, = -beta) and
+ * COV_GENE_MEAN (n_gene) of scdrs/method.py:377-395; host pointers; k = 0 switches it off */
+int scdrs_set_cov(scdrs_ctx* ctx, int32_t k, const double* cov_mat, const double* cov_beta,
+                  const double* gene_mean);
+
+/* ---- one trait, phase by phase (the multi-GPU driver runs collectives between phases) ------
+ * Phase 1 = _compute_raw_score x (1 + n_ctrl), scdrs/method.py:172-183, 312-402, plus the
+ * variance ratio of :186-195.  trait_genes[n_s] / trait_gw[n_s]: trait gene columns and their
+ * gene_weight in gene-name order; ctrl_genes[n_ctrl x n_s_ctrl]: control gene columns;
+ * ctrl_gw[n_s_ctrl]: the gene_weight each control position inherits (scdrs/method.py:305-307).
+ * n_s_ctrl == n_s unless some trait genes fall in no bin (NaN match key).  Host pointers.
+ * dev_colsum_out[1 + n_ctrl] receives this rank's column sums of the raw-score matrix. */
+int scdrs_trait_raw(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                    const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                    const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
+                    double* dev_colsum_out);
+/* Phase 2 = first gene-set alignment + cell-wise standardisation, scdrs/method.py:526-548.
+ * dev_colsum: column sums over ALL ranks; n_cell_total: cells over all ranks.
+ * Outputs (device, 1 + n_ctrl each): column sums and column minima of the standardised scores. */
+int scdrs_trait_rowstats(scdrs_ctx* ctx, const double* dev_colsum, int64_t n_cell_total,
+                         double* dev_colsum2_out, double* dev_colmin_out);
+/* Phase 3 = second alignment + zero rule for the trait column, scdrs/method.py:564-582.
+ * dev_colsum2 / dev_colmin: all-rank sums / minima.  dev_query_out[n_cell]: this rank's final
+ * normalised trait scores (float32). */
+int scdrs_trait_queries(scdrs_ctx* ctx, const double* dev_colsum2, const double* dev_colmin,
+                        float* dev_query_out);
+/* Phase 4 = mc_pval counts (scdrs/method.py:205) and the pooled empirical null
+ * (_get_p_from_empi_null, scdrs/method.py:601-632): radix-sorts all ranks' queries, then
+ * bucket-counts this rank's n_cell x n_ctrl null values between consecutive sorted queries.
+ * dev_hist_out[n_query_all + 1] (uint64): dev_hist_out[p] = #{local null with exactly p queries <= it}. */
+int scdrs_trait_count(scdrs_ctx* ctx, const float* dev_query_all, int64_t n_query_all,
+                      unsigned long long* dev_hist_out);
+/* Phase 5: suffix-sum the all-rank histogram into #{null >= t} and copy results to the host.
+ * query_offset: position of this rank's first cell inside dev_query_all.  Host outputs:
+ * raw_score[n_cell] f64, norm_score[n_cell] f32, mc_count[n_cell] i32 = #{ctrl_norm >= norm},
+ * ge_count[n_cell] i64 = #{pooled null >= norm}; ctrl_raw / ctrl_norm [n_cell x n_ctrl] f32 or NULL. */
+int scdrs_trait_finish(scdrs_ctx* ctx, const unsigned long long* dev_hist_all, int64_t n_query_all,
+                       int64_t query_offset, int64_t n_null_total, double* raw_score,
+                       float* norm_score, int32_t* mc_count, int64_t* ge_count, float* ctrl_raw,
+                       float* ctrl_norm);
+
+/* ---- one trait, single GPU: phases 1-5 back to back = scdrs.method.score_cell's device part */
+int scdrs_score_trait(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                      const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                      const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
+                      double* raw_score, float* norm_score, int32_t* mc_count, int64_t* ge_count,
+                      float* ctrl_raw, float* ctrl_norm);
+
+/* ---- the reference's helper functions as stand-alone calls (host buffers) ------------------ */
+/* _compute_raw_score (scdrs/method.py:377-400) for n_set explicit gene sets with FINAL weights
+ * w[n_set x n_s] (already normalised); raw_out[n_cell x n_set] f64. */
+int scdrs_compute_raw_score(scdrs_ctx* ctx, int32_t n_set, int32_t n_s, const int32_t* genes,
+                            const double* w, double* raw_out);
+/* _correct_background (scdrs/method.py:482-598): v_raw[n_cell], mat_ctrl[n_cell x n_ctrl],
+ * var_ratio[n_ctrl] -> v_norm[n_cell], mat_norm[n_cell x n_ctrl] (all f64 host) */
+int scdrs_correct_background(scdrs_ctx* ctx, int64_t n_cell, int32_t n_ctrl, const double* v_raw,
+                             const double* mat_ctrl, const double* var_ratio, double* v_norm,
+                             double* mat_norm);
+/* _get_p_from_empi_null (scdrs/method.py:601-632): ge_count[i] = #{null >= t[i]};
+ * p = (ge_count + 1) / (n_null + 1).  f32 and f64 key variants. */
+int scdrs_empi_null_count_f32(scdrs_ctx* ctx, int64_t n_t, const float* t, int64_t n_null,
+                              const float* null_vals, int64_t* ge_count);
+int scdrs_empi_null_count_f64(scdrs_ctx* ctx, int64_t n_t, const double* t, int64_t n_null,
+                              const double* null_vals, int64_t* ge_count);
+/* pp.compute_stats reductions (scdrs/pp.py:353-373, 409-417, 467-641) over the resident CSR,
+ * of T(X + COV_MAT*COV_BETA + COV_GENE_MEAN) when covariates are set (implicit mode) else T(X);
+ * T = identity (transform 0) or expm1 (transform 1).  cell_weight[n_cell] or NULL.
+ * Outputs (host f64): gene_sum[n_gene] = sum_c w_c T(x), gene_sumsq[n_gene] = sum_c w_c T(x)^2,
+ * cell_sum[n_cell], cell_sumsq[n_cell] (unweighted row sums; NULL to skip). */
+int scdrs_gene_cell_stats(scdrs_ctx* ctx, int32_t transform, const double* cell_weight,
+                          double* gene_sum, double* gene_sumsq, double* cell_sum,
+                          double* cell_sumsq);
+
+/* ---- host code: the random draws of _select_ctrl_geneset (scdrs/method.py:276, 295-307) --------
+ * numpy-legacy MT19937 seeded with `seed`, bins visited in the given order; for every bin b with
+ * bin_ntrait[b] > 0 and every control set i: permutation(len(bin b))[:bin_ntrait[b]] indexes
+ * bin_genes[bin_ptr[b] .. bin_ptr[b+1]) (gene columns ordered by gene name).  Writes
+ * ctrl_genes[n_ctrl x n_s]; bit-identical to np.random.seed(seed) + np.random.choice(...). */
+int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr, const int32_t* bin_genes,
+                      const int32_t* bin_ntrait, int32_t n_ctrl, int32_t n_s, int32_t* ctrl_genes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDRS_B200_H */

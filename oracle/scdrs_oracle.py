@@ -249,3 +249,110 @@ def score_cell(
             v_norm=v_norm, trait_w=v_w, ctrl_w=mat_w,
         )
     return df
+
+
+# ----------------------------------------------------------------------------------------------
+# preprocessing statistics                                                 scdrs/pp.py:63-641
+# ----------------------------------------------------------------------------------------------
+def mean_var(X, axis=0, weights=None):
+    """Restates _get_mean_var (scdrs/pp.py:467-517) in float64 on a dense copy."""
+    A = np.asarray(X.toarray() if sparse.issparse(X) else X, dtype=np.float64)
+    if weights is None:
+        return A.mean(axis=axis), A.var(axis=axis)
+    w = np.asarray(weights, dtype=np.float64)
+    m = np.average(A, axis=axis, weights=w)
+    return m, np.average(A * A, axis=axis, weights=w) - m ** 2
+
+
+def corrected_matrix(adata):
+    """Dense ``X + COV_MAT @ COV_BETA.T + COV_GENE_MEAN`` (scdrs/pp.py:556, :613-617) or X itself."""
+    param = adata.uns.get("SCDRS_PARAM", {})
+    X = adata.X
+    A = np.asarray(X.toarray() if sparse.issparse(X) else X, dtype=np.float64)
+    if param.get("FLAG_SPARSE") and param.get("FLAG_COV"):
+        cols = list(param["COV_MAT"])
+        C = param["COV_MAT"].loc[list(adata.obs_names), cols].values.astype(np.float64)
+        B = param["COV_BETA"].loc[list(adata.var_names), cols].values.astype(np.float64)
+        mu = param["COV_GENE_MEAN"].loc[list(adata.var_names)].values.astype(np.float64)
+        A = A + C @ B.T + mu
+    return A
+
+
+def compute_stats(adata, implicit_cov_corr=False, cell_weight=None, n_mean_bin=20, n_var_bin=20, loess_impl=None):
+    """Restates compute_stats (scdrs/pp.py:337-419) on a dense float64 copy of the corrected matrix
+    (small inputs only).  ``loess_impl`` stands in for skmisc.loess.loess."""
+    A = corrected_matrix(adata) if implicit_cov_corr else np.asarray(
+        adata.X.toarray() if sparse.issparse(adata.X) else adata.X, dtype=np.float64)
+    df_gene = pd.DataFrame(index=adata.var_names,
+                           columns=["mean", "var", "var_tech", "ct_mean", "ct_var", "ct_var_tech", "mean_var"])
+    df_cell = pd.DataFrame(index=adata.obs_names, columns=["mean", "var"])
+    df_gene["mean"], df_gene["var"] = mean_var(A, 0, cell_weight)                       # :353/:368
+    df_gene["ct_mean"], df_gene["ct_var"] = mean_var(np.expm1(A), 0, cell_weight)       # :359-364/:371
+    ct_mean, ct_var = df_gene["ct_mean"].values.astype(float), df_gene["ct_var"].values.astype(float)
+    not_const = ct_var > 0                                                               # :376-380
+    if (ct_mean <= 0).sum() > 0:
+        not_const = not_const & (ct_mean > 0)
+    est = np.zeros(A.shape[1])
+    model = loess_impl(np.log10(ct_mean[not_const]), np.log10(ct_var[not_const]), span=0.3, degree=2)
+    model.fit()
+    est[not_const] = model.outputs.fitted_values                                         # :384-386
+    df_gene["ct_var_tech"] = 10 ** est
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vt = df_gene["var"].values.astype(float) * df_gene["ct_var_tech"].values / ct_var   # :389
+    vt[np.isnan(vt)] = 0                                                                 # :390
+    df_gene["var_tech"] = vt
+    n_bin_max = int(np.floor(np.sqrt(A.shape[1] / 10)))                                  # :393-399
+    if n_mean_bin > n_bin_max or n_var_bin > n_bin_max:
+        n_mean_bin = n_var_bin = n_bin_max
+    mbin = pd.qcut(df_gene["mean"].astype(float), n_mean_bin, labels=False, duplicates="drop")   # :400
+    labels = np.full(A.shape[1], "", dtype=object)
+    for b in sorted(set(mbin)):                                                          # :402-407
+        sel = (mbin == b).values
+        vbin = pd.qcut(df_gene.loc[sel, "var"].astype(float), n_var_bin, labels=False, duplicates="drop")
+        labels[sel] = ["%d.%d" % (b, x) for x in vbin]
+    df_gene["mean_var"] = labels
+    df_cell["mean"], df_cell["var"] = mean_var(A, 1)                                     # :409-417
+    return df_gene, df_cell
+
+
+def reg_out(Y, X):
+    """Restates reg_out (scdrs/pp.py:425-464)."""
+    X = np.asarray(X, dtype=np.float64).reshape(len(X), -1)
+    Y2 = np.asarray(Y, dtype=np.float64).reshape(len(Y), -1)
+    n = Y2.shape[0]
+    coef = np.linalg.solve(X.T @ X / n, X.T @ Y2 / n)
+    R = Y2 - X @ coef
+    return R.reshape(-1) if R.shape[1] == 1 else R
+
+
+def preprocess(adata, cov=None, adj_prop=None, n_mean_bin=20, n_var_bin=20, loess_impl=None):
+    """Restates preprocess (scdrs/pp.py:165-271); numeric covariates only; writes SCDRS_PARAM."""
+    n_cell, n_gene = adata.shape
+    flag_sparse, flag_cov = sparse.issparse(adata.X), cov is not None
+    adata.uns["SCDRS_PARAM"] = {"FLAG_SPARSE": flag_sparse, "FLAG_COV": flag_cov,
+                                "FLAG_ADJ_PROP": adj_prop is not None}
+    if flag_sparse:
+        adata.X = sparse.csr_matrix(adata.X)
+    if flag_cov:
+        df_cov = pd.DataFrame(index=adata.obs_names).join(cov)                          # :195-198
+        df_cov = df_cov.fillna(df_cov.mean())
+        if (reg_out(np.ones(n_cell), df_cov.values) ** 2).mean() > 0.01:                # :201-203
+            df_cov["SCDRS_CONST"] = 1
+        C = df_cov.values.astype(np.float64)
+        gmean = np.asarray(adata.X.mean(axis=0)).reshape(-1)                            # :206
+        if flag_sparse:
+            beta = np.linalg.solve(C.T @ C / n_cell, np.asarray((adata.X.T @ C).T) / n_cell)   # :209-212
+            adata.uns["SCDRS_PARAM"]["COV_MAT"] = df_cov
+            adata.uns["SCDRS_PARAM"]["COV_BETA"] = pd.DataFrame(-beta.T, index=adata.var_names, columns=df_cov.columns)
+            adata.uns["SCDRS_PARAM"]["COV_GENE_MEAN"] = pd.Series(gmean, index=adata.var_names)
+        else:
+            adata.X = reg_out(np.asarray(adata.X), C) + gmean                           # :223-224
+    w = None
+    if adj_prop is not None:                                                             # :242-257
+        size = adata.obs[adj_prop].value_counts()
+        size = size.clip(lower=int(0.01 * size.max()))      # the docstring's floor (:93-94)
+        w = (n_cell / size.reindex(adata.obs[adj_prop].values).values).astype(np.float64)
+        w = w / w.mean()
+    df_gene, df_cell = compute_stats(adata, bool(flag_sparse and flag_cov), w, n_mean_bin, n_var_bin, loess_impl)
+    adata.uns["SCDRS_PARAM"]["GENE_STATS"] = df_gene
+    adata.uns["SCDRS_PARAM"]["CELL_STATS"] = df_cell

@@ -1,0 +1,110 @@
+"""Per-AnnData device residency: the expression matrix is uploaded once and reused by every
+``score_cell`` / ``compute_stats`` call on the same object (the reference re-slices a CSC copy on
+every call, scdrs/method.py:98-99, :389-400)."""
+import weakref
+
+import numpy as np
+from scipy import sparse
+
+from . import _native
+
+_STATES = {}  # id(adata) -> DeviceState
+_DEFAULT_DEVICE = [0]
+
+
+def set_default_device(device):
+    """GPU index new device states are created on (one process per GPU under torchrun)."""
+    _DEFAULT_DEVICE[0] = int(device)
+
+
+def clear_device_cache():
+    """Drop every resident matrix (call after mutating ``adata.X`` in place)."""
+    for st in list(_STATES.values()):
+        st.close()
+    _STATES.clear()
+
+
+def _x_fingerprint(X):
+    if sparse.issparse(X):
+        return ("sp", id(X), id(X.data), X.shape, X.nnz, X.format)
+    return ("dn", id(X), X.shape, str(X.dtype))
+
+
+def to_csr_parts(X):
+    """(indptr int64, indices int32, data float32) of X; dense arrays keep only non-zeros."""
+    if not sparse.issparse(X):
+        X = sparse.csr_matrix(np.asarray(X))
+    elif not isinstance(X, sparse.csr_matrix):
+        X = sparse.csr_matrix(X)
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    return (
+        np.ascontiguousarray(X.indptr, dtype=np.int64),
+        np.ascontiguousarray(X.indices, dtype=np.int32),
+        np.ascontiguousarray(X.data, dtype=np.float32),
+    )
+
+
+class DeviceState:
+    def __init__(self, adata, device):
+        self.ctx = _native.Context(device)
+        self.x_fp = None
+        self.cov_fp = None
+        self.h2d_bytes = 0
+        self.bins_cache = {}
+
+    def close(self):
+        self.ctx.close()
+
+    def ensure_matrix(self, adata):
+        fp = _x_fingerprint(adata.X)
+        if fp != self.x_fp:
+            indptr, indices, data = to_csr_parts(adata.X)
+            self.ctx.set_csr_host(indptr, indices, data, adata.shape[1])
+            self.h2d_bytes += indptr.nbytes + indices.nbytes + data.nbytes
+            self.x_fp = fp
+            self.cov_fp = None
+        return self.ctx
+
+    def ensure_cov(self, adata, implicit):
+        """Upload COV_MAT / COV_BETA / COV_GENE_MEAN aligned to obs_names / var_names."""
+        if not implicit:
+            if self.cov_fp != "none":
+                self.ctx.set_cov(None)
+                self.cov_fp = "none"
+            return
+        param = adata.uns["SCDRS_PARAM"]
+        fp = (id(param["COV_MAT"]), id(param["COV_BETA"]), id(param["COV_GENE_MEAN"]),
+              param["COV_MAT"].shape, param["COV_BETA"].shape)
+        if fp == self.cov_fp:
+            return
+        cov_cols = list(param["COV_MAT"])
+        cov_mat = param["COV_MAT"].reindex(index=adata.obs_names, columns=cov_cols).values
+        cov_beta = param["COV_BETA"].reindex(index=adata.var_names, columns=cov_cols).values
+        gene_mean = param["COV_GENE_MEAN"].reindex(adata.var_names).values
+        cov_mat = np.ascontiguousarray(cov_mat, dtype=np.float64)
+        cov_beta = np.ascontiguousarray(cov_beta, dtype=np.float64)
+        gene_mean = np.ascontiguousarray(gene_mean, dtype=np.float64)
+        self.ctx.set_cov(cov_mat, cov_beta, gene_mean)
+        self.h2d_bytes += cov_mat.nbytes + cov_beta.nbytes + gene_mean.nbytes
+        self.cov_fp = fp
+
+
+def get_state(adata, device=None):
+    key = id(adata)
+    st = _STATES.get(key)
+    if st is None:
+        st = DeviceState(adata, _DEFAULT_DEVICE[0] if device is None else device)
+        _STATES[key] = st
+        try:
+            weakref.finalize(adata, _drop, key)
+        except TypeError:
+            pass
+    return st
+
+
+def _drop(key):
+    st = _STATES.pop(key, None)
+    if st is not None:
+        st.close()

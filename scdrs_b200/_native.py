@@ -1,0 +1,263 @@
+"""ctypes binding of ``libscdrs_b200.so`` (C ABI in ``include/scdrs_b200.h``).
+
+The product path has NO CPU fallback: if the library is missing or no B200 is visible, the
+first call raises ``RuntimeError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscdrs_b200.so")
+
+_lib = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_u64p = C.POINTER(C.c_uint64)
+
+# name -> (restype, argtypes); must list every symbol include/scdrs_b200.h declares
+SIGNATURES = {
+    "scdrs_last_error": (C.c_char_p, []),
+    "scdrs_abi_version": (C.c_int, []),
+    "scdrs_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "scdrs_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "scdrs_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "scdrs_ctx_sync": (C.c_int, [C.c_void_p]),
+    "scdrs_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "scdrs_ctx_last_timing": (C.c_int, [C.c_void_p, c_f32p, c_f32p]),
+    "scdrs_set_csr_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_set_csr_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_set_gene_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_set_cov": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_trait_raw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "scdrs_trait_rowstats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "scdrs_trait_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_trait_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "scdrs_trait_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_score_trait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_compute_raw_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_correct_background": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_empi_null_count_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "scdrs_empi_null_count_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
+}
+
+WEIGHT_OPT = {"uniform": 0, "vs": 1, "inv_std": 2}
+
+
+def lib():
+    """Load the shared library (once); raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "scdrs_b200: %s not found -- build it with `python -m scdrs_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("scdrs_b200: " + lib().scdrs_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Raw pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def as_c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One GPU context holding one resident expression matrix."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._L = lib()
+        check(self._L.scdrs_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+        self.n_cell = 0
+        self.n_gene = 0
+        self._keep = []  # arrays / tensors the device side borrows
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            self._L.scdrs_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- resident inputs --
+    def set_csr_host(self, indptr, indices, data, n_gene):
+        indptr = as_c(indptr, np.int64)
+        indices = as_c(indices, np.int32)
+        data = as_c(data, np.float32)
+        n_cell = indptr.shape[0] - 1
+        check(self._L.scdrs_set_csr_host(self._h, n_cell, int(n_gene), ptr(indptr), ptr(indices), ptr(data)))
+        self.n_cell, self.n_gene = n_cell, int(n_gene)
+        self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes
+
+    def set_csr_dev(self, n_cell, n_gene, d_indptr, d_indices, d_data, keep=()):
+        check(self._L.scdrs_set_csr_dev(self._h, int(n_cell), int(n_gene), int(d_indptr), int(d_indices), int(d_data)))
+        self.n_cell, self.n_gene = int(n_cell), int(n_gene)
+        self._keep = list(keep)
+
+    def set_gene_stats(self, var, var_tech):
+        var, var_tech = as_c(var, np.float64), as_c(var_tech, np.float64)
+        assert var.shape[0] == self.n_gene and var_tech.shape[0] == self.n_gene
+        check(self._L.scdrs_set_gene_stats(self._h, ptr(var), ptr(var_tech)))
+
+    def set_cov(self, cov_mat=None, cov_beta=None, gene_mean=None):
+        if cov_mat is None:
+            check(self._L.scdrs_set_cov(self._h, 0, None, None, None))
+            return
+        cov_mat, cov_beta = as_c(cov_mat, np.float64), as_c(cov_beta, np.float64)
+        gene_mean = as_c(gene_mean, np.float64)
+        k = cov_mat.shape[1]
+        assert cov_mat.shape == (self.n_cell, k) and cov_beta.shape == (self.n_gene, k)
+        check(self._L.scdrs_set_cov(self._h, k, ptr(cov_mat), ptr(cov_beta), ptr(gene_mean)))
+
+    def set_stream(self, cuda_stream):
+        check(self._L.scdrs_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def sync(self):
+        check(self._L.scdrs_ctx_sync(self._h))
+
+    def launch_count(self):
+        return int(self._L.scdrs_ctx_launch_count(self._h))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        check(self._L.scdrs_ctx_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- one trait, single GPU --
+    def score_trait(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_var_ratio,
+                    want_ctrl_raw=False, want_ctrl_norm=False):
+        trait_genes = as_c(trait_genes, np.int32)
+        ctrl_genes = as_c(ctrl_genes, np.int32)
+        trait_gw, ctrl_gw = as_c(trait_gw, np.float64), as_c(ctrl_gw, np.float64)
+        n_s = trait_genes.shape[0]
+        n_ctrl, n_sc = ctrl_genes.shape
+        assert ctrl_gw.shape[0] == n_sc and trait_gw.shape[0] == n_s
+        n = self.n_cell
+        out = dict(
+            raw_score=np.empty(n, np.float64), norm_score=np.empty(n, np.float32),
+            mc_count=np.empty(n, np.int32), ge_count=np.empty(n, np.int64),
+            ctrl_raw=np.empty((n, n_ctrl), np.float32) if want_ctrl_raw else None,
+            ctrl_norm=np.empty((n, n_ctrl), np.float32) if want_ctrl_norm else None,
+        )
+        check(self._L.scdrs_score_trait(
+            self._h, n_ctrl, n_s, n_sc, ptr(trait_genes), ptr(trait_gw), ptr(ctrl_genes), ptr(ctrl_gw),
+            WEIGHT_OPT[weight_opt], int(bool(use_var_ratio)), ptr(out["raw_score"]),
+            ptr(out["norm_score"]), ptr(out["mc_count"]), ptr(out["ge_count"]), ptr(out["ctrl_raw"]),
+            ptr(out["ctrl_norm"])))
+        return out
+
+    # -- phases (device pointers are plain ints) --
+    def trait_raw(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_var_ratio, d_colsum):
+        trait_genes, ctrl_genes = as_c(trait_genes, np.int32), as_c(ctrl_genes, np.int32)
+        trait_gw, ctrl_gw = as_c(trait_gw, np.float64), as_c(ctrl_gw, np.float64)
+        check(self._L.scdrs_trait_raw(self._h, ctrl_genes.shape[0], trait_genes.shape[0], ctrl_genes.shape[1], ptr(trait_genes),
+                                      ptr(trait_gw), ptr(ctrl_genes), ptr(ctrl_gw), WEIGHT_OPT[weight_opt],
+                                      int(bool(use_var_ratio)), int(d_colsum)))
+
+    def trait_rowstats(self, d_colsum, n_cell_total, d_colsum2, d_colmin):
+        check(self._L.scdrs_trait_rowstats(self._h, int(d_colsum), int(n_cell_total), int(d_colsum2), int(d_colmin)))
+
+    def trait_queries(self, d_colsum2, d_colmin, d_query):
+        check(self._L.scdrs_trait_queries(self._h, int(d_colsum2), int(d_colmin), int(d_query)))
+
+    def trait_count(self, d_query_all, n_query_all, d_hist):
+        check(self._L.scdrs_trait_count(self._h, int(d_query_all), int(n_query_all), int(d_hist)))
+
+    def trait_finish(self, d_hist_all, n_query_all, query_offset, n_null_total, n_ctrl,
+                     want_ctrl_raw=False, want_ctrl_norm=False):
+        n = self.n_cell
+        out = dict(
+            raw_score=np.empty(n, np.float64), norm_score=np.empty(n, np.float32),
+            mc_count=np.empty(n, np.int32), ge_count=np.empty(n, np.int64),
+            ctrl_raw=np.empty((n, n_ctrl), np.float32) if want_ctrl_raw else None,
+            ctrl_norm=np.empty((n, n_ctrl), np.float32) if want_ctrl_norm else None,
+        )
+        check(self._L.scdrs_trait_finish(
+            self._h, int(d_hist_all), int(n_query_all), int(query_offset), int(n_null_total),
+            ptr(out["raw_score"]), ptr(out["norm_score"]), ptr(out["mc_count"]), ptr(out["ge_count"]),
+            ptr(out["ctrl_raw"]), ptr(out["ctrl_norm"])))
+        return out
+
+    # -- stand-alone helpers --
+    def compute_raw_score(self, genes, w):
+        genes, w = as_c(genes, np.int32), as_c(w, np.float64)
+        if genes.ndim == 1:
+            genes, w = genes[None, :], w[None, :]
+        n_set, n_s = genes.shape
+        out = np.empty((self.n_cell, n_set), np.float64)
+        check(self._L.scdrs_compute_raw_score(self._h, n_set, n_s, ptr(genes), ptr(w), ptr(out)))
+        return out
+
+    def correct_background(self, v_raw, mat_ctrl, var_ratio):
+        v_raw, mat_ctrl = as_c(v_raw, np.float64), as_c(mat_ctrl, np.float64)
+        var_ratio = as_c(var_ratio, np.float64)
+        n_cell, n_ctrl = mat_ctrl.shape
+        v_norm, mat_norm = np.empty(n_cell, np.float64), np.empty((n_cell, n_ctrl), np.float64)
+        check(self._L.scdrs_correct_background(self._h, n_cell, n_ctrl, ptr(v_raw), ptr(mat_ctrl),
+                                               ptr(var_ratio), ptr(v_norm), ptr(mat_norm)))
+        return v_norm, mat_norm
+
+    def empi_null_count(self, v_t, v_null):
+        v_t, v_null = np.asarray(v_t), np.asarray(v_null)
+        f32 = v_t.dtype == np.float32 and v_null.dtype == np.float32
+        dt = np.float32 if f32 else np.float64
+        v_t, v_null = as_c(v_t.reshape(-1), dt), as_c(v_null.reshape(-1), dt)
+        out = np.empty(v_t.shape[0], np.int64)
+        fn = self._L.scdrs_empi_null_count_f32 if f32 else self._L.scdrs_empi_null_count_f64
+        check(fn(self._h, v_t.shape[0], ptr(v_t), v_null.shape[0], ptr(v_null), ptr(out)))
+        return out
+
+    def gene_cell_stats(self, transform, cell_weight=None, want_gene=True, want_cell=True):
+        w = None if cell_weight is None else as_c(cell_weight, np.float64)
+        gs = np.empty(self.n_gene) if want_gene else None
+        gq = np.empty(self.n_gene) if want_gene else None
+        cs = np.empty(self.n_cell) if want_cell else None
+        cq = np.empty(self.n_cell) if want_cell else None
+        check(self._L.scdrs_gene_cell_stats(self._h, int(transform), ptr(w), ptr(gs), ptr(gq), ptr(cs), ptr(cq)))
+        return gs, gq, cs, cq
+
+
+def select_ctrl(seed, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s):
+    """Host-only: numpy-legacy-RNG control gene draws (see include/scdrs_b200.h)."""
+    bin_ptr, bin_genes = as_c(bin_ptr, np.int32), as_c(bin_genes, np.int32)
+    bin_ntrait = as_c(bin_ntrait, np.int32)
+    out = np.empty((n_ctrl, n_s), np.int32)
+    check(lib().scdrs_select_ctrl(int(seed) & 0xFFFFFFFF, bin_ntrait.shape[0], ptr(bin_ptr), ptr(bin_genes),
+                                  ptr(bin_ntrait), int(n_ctrl), int(n_s), ptr(out)))
+    return out

@@ -1,0 +1,471 @@
+// C ABI (include/scdrs_b200.h): context management, host<->device staging and phase sequencing.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace scdrs {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (bytes <= cap) return 0;
+    if (p != nullptr) {
+        cudaError_t e = cudaFree(p);  // synchronises; contents are scratch
+        p = nullptr;
+        cap = 0;
+        if (e != cudaSuccess) {
+            set_error("cudaFree failed: %s", cudaGetErrorString(e));
+            return 1;
+        }
+    }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return 1;
+    }
+    cap = want;
+    return 0;
+}
+
+void DevBuf::release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int h2d(scdrs_ctx* c, DevBuf& buf, const void* host, size_t bytes) {
+    SCDRS_TRY(buf.reserve(bytes));
+    if (bytes) SCDRS_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int d2h(scdrs_ctx* c, void* host, const void* dev, size_t bytes) {
+    if (bytes) SCDRS_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+static void release_all(scdrs_ctx* c) {
+    DevBuf* bufs[] = {&c->own_indptr, &c->own_indices, &c->own_data, &c->var, &c->var_tech,
+                      &c->cov_mat, &c->cov_beta, &c->gene_mean, &c->set_genes, &c->set_gw, &c->set_w,
+                      &c->covM, &c->covm, &c->ratio_a, &c->w_ptr, &c->w_cursor, &c->w_col, &c->w_val,
+                      &c->dev_mat, &c->row_ref, &c->partial, &c->colmean, &c->col2, &c->colmin,
+                      &c->row_mean, &c->row_istd, &c->scalars, &c->query, &c->mc_count, &c->norm_mat,
+                      &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],
+                      &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
+                      &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage};
+    for (DevBuf* b : bufs) b->release();
+}
+
+}  // namespace scdrs
+
+using namespace scdrs;
+
+#define CTX_GUARD(c)                                                       \
+    SCDRS_CHECK((c) != nullptr, "null context");                           \
+    SCDRS_CUDA(cudaSetDevice((c)->device))
+
+template <typename F>
+static int empi_null_count(scdrs_ctx* c, int64_t n_t, const F* t, int64_t n_null, const F* null_vals,
+                           int64_t* ge_count) {
+    SCDRS_CHECK(n_t >= 1 && n_null >= 0, "empty input");
+    SCDRS_CHECK(t && ge_count && (null_vals || n_null == 0), "null pointer");
+    scdrs_ctx s;
+    s.device = c->device;
+    s.stream = c->stream;
+    DevBuf d_t, d_n, d_ge;
+    int rc = 1;
+    do {
+        if (h2d(&s, d_t, t, (size_t)n_t * sizeof(F)) || h2d(&s, d_n, null_vals, (size_t)n_null * sizeof(F)) ||
+            d_ge.reserve((size_t)n_t * sizeof(long long))) break;
+        int r2;
+        if (sizeof(F) == 4)
+            r2 = null_count_generic_f32(&s, n_t, (const float*)d_t.p, n_null, (const float*)d_n.p, d_ge.as<long long>());
+        else
+            r2 = null_count_generic_f64(&s, n_t, (const double*)d_t.p, n_null, (const double*)d_n.p, d_ge.as<long long>());
+        if (r2) break;
+        if (d2h(&s, ge_count, d_ge.p, (size_t)n_t * sizeof(int64_t))) break;
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { set_error("stream sync failed"); break; }
+        rc = 0;
+    } while (0);
+    d_t.release(); d_n.release(); d_ge.release();
+    c->launches += s.launches;
+    release_all(&s);
+    return rc;
+}
+
+extern "C" {
+
+const char* scdrs_last_error(void) { return g_err; }
+int scdrs_abi_version(void) { return 1; }
+
+int scdrs_ctx_create(int device, scdrs_ctx** out) {
+    SCDRS_CHECK(out != nullptr, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    SCDRS_CHECK(e == cudaSuccess && n > 0,
+                "no CUDA device available (%s); scdrs_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    SCDRS_CHECK(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    SCDRS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SCDRS_CUDA(cudaGetDeviceProperties(&prop, device));
+    SCDRS_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+    scdrs_ctx* c = new (std::nothrow) scdrs_ctx();
+    SCDRS_CHECK(c != nullptr, "out of host memory");
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        set_error("cudaStreamCreate failed");
+        return 1;
+    }
+    c->own_stream = true;
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
+    c->timed_spmm = c->timed_trait = true;
+    *out = c;
+    return 0;
+}
+
+int scdrs_ctx_destroy(scdrs_ctx* c) {
+    if (c == nullptr) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    release_all(c);
+    for (int i = 0; i < 4; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int scdrs_ctx_set_stream(scdrs_ctx* c, void* cuda_stream) {
+    CTX_GUARD(c);
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return 0;
+}
+
+int scdrs_ctx_sync(scdrs_ctx* c) {
+    CTX_GUARD(c);
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int64_t scdrs_ctx_launch_count(scdrs_ctx* c) { return c ? c->launches : -1; }
+
+int scdrs_ctx_last_timing(scdrs_ctx* c, float* spmm_ms, float* trait_ms) {
+    CTX_GUARD(c);
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    if (spmm_ms) {
+        *spmm_ms = -1.f;
+        if (cudaEventElapsedTime(spmm_ms, c->ev[0], c->ev[1]) != cudaSuccess) { *spmm_ms = -1.f; cudaGetLastError(); }
+    }
+    if (trait_ms) {
+        *trait_ms = -1.f;
+        if (cudaEventElapsedTime(trait_ms, c->ev[2], c->ev[3]) != cudaSuccess) { *trait_ms = -1.f; cudaGetLastError(); }
+    }
+    return 0;
+}
+
+// ---- resident inputs ---------------------------------------------------------------------------
+static int check_shape(int64_t n_cell, int32_t n_gene) {
+    SCDRS_CHECK(n_cell >= 1, "n_cell must be >= 1");
+    SCDRS_CHECK(n_gene >= 1, "n_gene must be >= 1");
+    return 0;
+}
+
+int scdrs_set_csr_host(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_t* indptr,
+                       const int32_t* indices, const float* data) {
+    CTX_GUARD(c);
+    SCDRS_TRY(check_shape(n_cell, n_gene));
+    SCDRS_CHECK(indptr && (indices || indptr[n_cell] == 0), "null CSR arrays");
+    const int64_t nnz = indptr[n_cell];
+    SCDRS_CHECK(indptr[0] == 0 && nnz >= 0, "malformed indptr");
+    SCDRS_TRY(h2d(c, c->own_indptr, indptr, (size_t)(n_cell + 1) * sizeof(int64_t)));
+    SCDRS_TRY(h2d(c, c->own_indices, indices, (size_t)nnz * sizeof(int32_t)));
+    SCDRS_TRY(h2d(c, c->own_data, data, (size_t)nnz * sizeof(float)));
+    c->indptr = c->own_indptr.as<int64_t>();
+    c->indices = c->own_indices.as<int32_t>();
+    c->data = c->own_data.as<float>();
+    c->n_cell = n_cell;
+    c->n_gene = n_gene;
+    c->nnz = nnz;
+    c->trait_ready = false;
+    c->have_stats = false;
+    c->k = 0;
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_t* dev_indptr,
+                      const int32_t* dev_indices, const float* dev_data) {
+    CTX_GUARD(c);
+    SCDRS_TRY(check_shape(n_cell, n_gene));
+    SCDRS_CHECK(dev_indptr != nullptr, "null CSR arrays");
+    int64_t nnz = 0;
+    SCDRS_CUDA(cudaMemcpyAsync(&nnz, dev_indptr + n_cell, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    c->indptr = dev_indptr;
+    c->indices = dev_indices;
+    c->data = dev_data;
+    c->n_cell = n_cell;
+    c->n_gene = n_gene;
+    c->nnz = nnz;
+    c->trait_ready = false;
+    c->have_stats = false;
+    c->k = 0;
+    return 0;
+}
+
+int scdrs_set_gene_stats(scdrs_ctx* c, const double* var, const double* var_tech) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "set the expression matrix first");
+    SCDRS_CHECK(var && var_tech, "null gene statistics");
+    SCDRS_TRY(h2d(c, c->var, var, (size_t)c->n_gene * sizeof(double)));
+    SCDRS_TRY(h2d(c, c->var_tech, var_tech, (size_t)c->n_gene * sizeof(double)));
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_stats = true;
+    return 0;
+}
+
+int scdrs_set_cov(scdrs_ctx* c, int32_t k, const double* cov_mat, const double* cov_beta,
+                  const double* gene_mean) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "set the expression matrix first");
+    SCDRS_CHECK(k >= 0 && k <= 1024, "number of covariates %d out of range", k);
+    if (k > 0) {
+        SCDRS_CHECK(cov_mat && cov_beta && gene_mean, "null covariate arrays");
+        SCDRS_TRY(h2d(c, c->cov_mat, cov_mat, (size_t)c->n_cell * k * sizeof(double)));
+        SCDRS_TRY(h2d(c, c->cov_beta, cov_beta, (size_t)c->n_gene * k * sizeof(double)));
+        SCDRS_TRY(h2d(c, c->gene_mean, gene_mean, (size_t)c->n_gene * sizeof(double)));
+        SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->k = k;
+    c->trait_ready = false;
+    return 0;
+}
+
+// ---- phases -------------------------------------------------------------------------------------
+int scdrs_trait_raw(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                    const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                    const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
+                    double* dev_colsum_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(trait_genes && trait_gw && (n_ctrl == 0 || n_s_ctrl == 0 || (ctrl_genes && ctrl_gw)), "null gene-set arrays");
+    SCDRS_CHECK(dev_colsum_out != nullptr, "null output");
+    SCDRS_TRY(trait_prepare(c, n_ctrl, n_s, n_s_ctrl, trait_genes, trait_gw, ctrl_genes, ctrl_gw,
+                            weight_opt, use_var_ratio));
+    SCDRS_TRY(spmm_score(c));
+    return bg_colsum(c, dev_colsum_out);
+}
+
+int scdrs_trait_rowstats(scdrs_ctx* c, const double* dev_colsum, int64_t n_cell_total,
+                         double* dev_colsum2_out, double* dev_colmin_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(dev_colsum && dev_colsum2_out && dev_colmin_out, "null pointer");
+    return bg_rowstats(c, dev_colsum, n_cell_total, dev_colsum2_out, dev_colmin_out);
+}
+
+int scdrs_trait_queries(scdrs_ctx* c, const double* dev_colsum2, const double* dev_colmin,
+                        float* dev_query_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(dev_colsum2 && dev_colmin, "null pointer");
+    SCDRS_TRY(c->query.reserve((size_t)c->n_cell * sizeof(float)));
+    SCDRS_TRY(bg_queries(c, dev_colsum2, dev_colmin, c->query.as<float>()));
+    if (dev_query_out != nullptr && dev_query_out != c->query.as<float>())
+        SCDRS_CUDA(cudaMemcpyAsync(dev_query_out, c->query.p, (size_t)c->n_cell * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+static int trait_count_impl(scdrs_ctx* c, const float* dev_query_all, int64_t n_query_all,
+                            unsigned long long* dev_hist_out, bool write_norm) {
+    SCDRS_CHECK(n_query_all >= c->n_cell, "fewer queries than local cells");
+    SCDRS_TRY(null_prepare_queries(c, dev_query_all, n_query_all));
+    return null_count_pass(c, dev_hist_out, n_query_all, write_norm);
+}
+
+int scdrs_trait_count(scdrs_ctx* c, const float* dev_query_all, int64_t n_query_all,
+                      unsigned long long* dev_hist_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(dev_query_all && dev_hist_out, "null pointer");
+    // the normalised control matrix is always kept in the phase API (finish may ask for it)
+    return trait_count_impl(c, dev_query_all, n_query_all, dev_hist_out, true);
+}
+
+int scdrs_trait_finish(scdrs_ctx* c, const unsigned long long* dev_hist_all, int64_t n_query_all,
+                       int64_t query_offset, int64_t n_null_total, double* raw_score,
+                       float* norm_score, int32_t* mc_count, int64_t* ge_count, float* ctrl_raw,
+                       float* ctrl_norm) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(dev_hist_all != nullptr, "null pointer");
+    const int64_t n = c->n_cell;
+    SCDRS_CHECK(query_offset >= 0 && query_offset + n <= n_query_all, "query_offset out of range");
+    SCDRS_TRY(c->ge_local.reserve((size_t)n * sizeof(long long)));
+    SCDRS_TRY(null_finish(c, dev_hist_all, n_query_all, query_offset, n_null_total, n,
+                          c->ge_local.as<long long>()));
+    if (ge_count) SCDRS_TRY(d2h(c, ge_count, c->ge_local.p, (size_t)n * sizeof(int64_t)));
+    if (norm_score) SCDRS_TRY(d2h(c, norm_score, c->query.p, (size_t)n * sizeof(float)));
+    if (mc_count) SCDRS_TRY(d2h(c, mc_count, c->mc_count.p, (size_t)n * sizeof(int32_t)));
+    if (raw_score || ctrl_raw) {
+        const size_t need = (size_t)n * sizeof(double) + (ctrl_raw ? (size_t)n * c->n_ctrl * sizeof(float) : 0);
+        SCDRS_TRY(c->stage.reserve(need));
+        double* d_raw = c->stage.as<double>();
+        float* d_ctrl = ctrl_raw ? reinterpret_cast<float*>(d_raw + n) : nullptr;
+        SCDRS_TRY(bg_export_raw(c, d_raw, d_ctrl));
+        if (raw_score) SCDRS_TRY(d2h(c, raw_score, d_raw, (size_t)n * sizeof(double)));
+        if (ctrl_raw) SCDRS_TRY(d2h(c, ctrl_raw, d_ctrl, (size_t)n * c->n_ctrl * sizeof(float)));
+    }
+    if (ctrl_norm) {
+        SCDRS_CHECK(c->norm_mat.p != nullptr, "normalised control scores were not kept");
+        SCDRS_TRY(d2h(c, ctrl_norm, c->norm_mat.p, (size_t)n * c->n_ctrl * sizeof(float)));
+    }
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int scdrs_score_trait(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                      const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                      const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
+                      double* raw_score, float* norm_score, int32_t* mc_count, int64_t* ge_count,
+                      float* ctrl_raw, float* ctrl_norm) {
+    CTX_GUARD(c);
+    const int ncol = n_ctrl + 1;
+    SCDRS_CHECK(ncol >= 1, "n_ctrl < 0");
+    SCDRS_TRY(c->x_colsum.reserve(ncol * sizeof(double)));
+    SCDRS_TRY(c->x_col2.reserve(ncol * sizeof(double)));
+    SCDRS_TRY(c->x_colmin.reserve(ncol * sizeof(double)));
+    SCDRS_TRY(c->x_hist.reserve((size_t)(c->n_cell + 1) * sizeof(unsigned long long)));
+    if (c->timed_trait) SCDRS_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    SCDRS_TRY(scdrs_trait_raw(c, n_ctrl, n_s, n_s_ctrl, trait_genes, trait_gw, ctrl_genes, ctrl_gw,
+                              weight_opt, use_var_ratio, c->x_colsum.as<double>()));
+    SCDRS_TRY(scdrs_trait_rowstats(c, c->x_colsum.as<double>(), c->n_cell, c->x_col2.as<double>(),
+                                   c->x_colmin.as<double>()));
+    SCDRS_TRY(scdrs_trait_queries(c, c->x_col2.as<double>(), c->x_colmin.as<double>(), nullptr));
+    SCDRS_TRY(trait_count_impl(c, c->query.as<float>(), c->n_cell,
+                               c->x_hist.as<unsigned long long>(), ctrl_norm != nullptr));
+    const int rc = scdrs_trait_finish(c, c->x_hist.as<unsigned long long>(), c->n_cell, 0,
+                                      (int64_t)c->n_cell * n_ctrl, raw_score, norm_score, mc_count,
+                                      ge_count, ctrl_raw, ctrl_norm);
+    if (c->timed_trait) cudaEventRecord(c->ev[3], c->stream);
+    return rc;
+}
+
+// ---- stand-alone helpers --------------------------------------------------------------------------
+int scdrs_compute_raw_score(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
+                            const double* w, double* raw_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(genes && w && raw_out, "null pointer");
+    SCDRS_TRY(explicit_prepare(c, n_set, n_s, genes, w));
+    SCDRS_TRY(spmm_score(c));
+    // export as f64 [n_cell x n_set]: column 0 through raw_score, the rest through ctrl_raw (f32)
+    // would lose precision, so unpack on the host from the packed representation instead.
+    const int64_t n = c->n_cell;
+    std::vector<float> dev((size_t)n * c->ld);
+    std::vector<double> ref((size_t)n);
+    SCDRS_TRY(d2h(c, dev.data(), c->dev_mat.p, dev.size() * sizeof(float)));
+    SCDRS_TRY(d2h(c, ref.data(), c->row_ref.p, ref.size() * sizeof(double)));
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t r = 0; r < n; ++r)
+        for (int j = 0; j < n_set; ++j) {
+            const float d = dev[(size_t)r * c->ld + j];
+            raw_out[(size_t)r * n_set + j] = (d != d) ? 0.0 : ref[r] + (double)d;
+        }
+    return 0;
+}
+
+int scdrs_correct_background(scdrs_ctx* c, int64_t n_cell, int32_t n_ctrl, const double* v_raw,
+                             const double* mat_ctrl, const double* var_ratio, double* v_norm,
+                             double* mat_norm) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(n_cell >= 1 && n_ctrl >= 1, "empty input");
+    SCDRS_CHECK(v_raw && mat_ctrl && var_ratio && v_norm && mat_norm, "null pointer");
+    // scratch context sharing the device and stream, so the caller's resident state is untouched
+    scdrs_ctx t;
+    t.device = c->device;
+    t.stream = c->stream;
+    t.n_cell = n_cell;
+    int rc = 1;
+    do {
+        DevBuf d_v, d_m, d_r;
+        auto cleanup = [&]() { d_v.release(); d_m.release(); d_r.release(); };
+        const int ncol = n_ctrl + 1;
+        if (h2d(&t, d_v, v_raw, (size_t)n_cell * sizeof(double)) ||
+            h2d(&t, d_m, mat_ctrl, (size_t)n_cell * n_ctrl * sizeof(double)) ||
+            h2d(&t, d_r, var_ratio, (size_t)n_ctrl * sizeof(double))) { cleanup(); break; }
+        if (bg_pack_dense(&t, n_cell, n_ctrl, d_v.as<double>(), d_m.as<double>(), d_r.as<double>())) { cleanup(); break; }
+        t.trait_ready = true;
+        if (t.x_colsum.reserve(ncol * 8) || t.x_col2.reserve(ncol * 8) || t.x_colmin.reserve(ncol * 8) ||
+            t.x_hist.reserve((size_t)(n_cell + 1) * 8) || t.query.reserve((size_t)n_cell * 4)) { cleanup(); break; }
+        if (bg_colsum(&t, t.x_colsum.as<double>()) ||
+            bg_rowstats(&t, t.x_colsum.as<double>(), n_cell, t.x_col2.as<double>(), t.x_colmin.as<double>()) ||
+            bg_queries(&t, t.x_col2.as<double>(), t.x_colmin.as<double>(), t.query.as<float>()) ||
+            null_prepare_queries(&t, t.query.as<float>(), n_cell) ||
+            null_count_pass(&t, t.x_hist.as<unsigned long long>(), n_cell, true)) { cleanup(); break; }
+        std::vector<float> q((size_t)n_cell), m((size_t)n_cell * n_ctrl);
+        if (d2h(&t, q.data(), t.query.p, q.size() * 4) || d2h(&t, m.data(), t.norm_mat.p, m.size() * 4)) { cleanup(); break; }
+        if (cudaStreamSynchronize(t.stream) != cudaSuccess) { set_error("stream sync failed"); cleanup(); break; }
+        for (size_t i = 0; i < q.size(); ++i) v_norm[i] = (double)q[i];
+        for (size_t i = 0; i < m.size(); ++i) mat_norm[i] = (double)m[i];
+        cleanup();
+        rc = 0;
+    } while (0);
+    c->launches += t.launches;
+    release_all(&t);
+    return rc;
+}
+
+int scdrs_empi_null_count_f32(scdrs_ctx* c, int64_t n_t, const float* t, int64_t n_null,
+                              const float* null_vals, int64_t* ge_count) {
+    CTX_GUARD(c);
+    return empi_null_count<float>(c, n_t, t, n_null, null_vals, ge_count);
+}
+
+int scdrs_empi_null_count_f64(scdrs_ctx* c, int64_t n_t, const double* t, int64_t n_null,
+                              const double* null_vals, int64_t* ge_count) {
+    CTX_GUARD(c);
+    return empi_null_count<double>(c, n_t, t, n_null, null_vals, ge_count);
+}
+
+int scdrs_gene_cell_stats(scdrs_ctx* c, int32_t transform, const double* cell_weight,
+                          double* gene_sum, double* gene_sumsq, double* cell_sum,
+                          double* cell_sumsq) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    const int64_t n = c->n_cell;
+    const int g = c->n_gene;
+    DevBuf d_w;
+    if (cell_weight) SCDRS_TRY(h2d(c, d_w, cell_weight, (size_t)n * sizeof(double)));
+    const bool wg = gene_sum != nullptr, wc = cell_sum != nullptr;
+    SCDRS_TRY(c->stage.reserve(((size_t)2 * g + (size_t)2 * n) * sizeof(double)));
+    double* d_gs = c->stage.as<double>();
+    double* d_gq = d_gs + g;
+    double* d_cs = d_gq + g;
+    double* d_cq = d_cs + n;
+    int rc = gene_cell_stats(c, transform, cell_weight ? d_w.as<double>() : nullptr, wg ? d_gs : nullptr,
+                             wg ? d_gq : nullptr, wc ? d_cs : nullptr, wc ? d_cq : nullptr);
+    if (rc == 0 && wg) rc = d2h(c, gene_sum, d_gs, (size_t)g * 8) || d2h(c, gene_sumsq, d_gq, (size_t)g * 8);
+    if (rc == 0 && wc) rc = d2h(c, cell_sum, d_cs, (size_t)n * 8) || d2h(c, cell_sumsq, d_cq, (size_t)n * 8);
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("stream sync failed"); rc = 1; }
+    d_w.release();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Internal declarations shared by the kernel translation units.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/scdrs_b200.h"
+
+namespace scdrs {
+
+void set_error(const char* fmt, ...);
+
+#define SCDRS_CUDA(call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            scdrs::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,           \
+                             cudaGetErrorString(e__));                                    \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define SCDRS_CHECK(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            scdrs::set_error(__VA_ARGS__);     \
+            return 1;                          \
+        }                                      \
+    } while (0)
+
+#define SCDRS_TRY(expr)        \
+    do {                       \
+        if ((expr) != 0) return 1; \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kNumSM = 148;  // B200
+
+}  // namespace scdrs
+
+struct scdrs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed_spmm = false, timed_trait = false;
+
+    // resident expression matrix (CSR)
+    int64_t n_cell = 0, nnz = 0;
+    int32_t n_gene = 0;
+    const int64_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const float* data = nullptr;
+    scdrs::DevBuf own_indptr, own_indices, own_data;
+
+    // gene-level vectors
+    scdrs::DevBuf var, var_tech;
+    bool have_stats = false;
+    int32_t k = 0;  // number of covariates (0 = normal mode)
+    scdrs::DevBuf cov_mat, cov_beta, gene_mean;
+
+    // per-trait state
+    int32_t n_ctrl = 0, n_s = 0, n_sc = 0, ncol = 0, ld = 0;  // n_s: trait set size, n_sc: control set size
+    bool trait_ready = false;
+    scdrs::DevBuf set_genes, set_gw, set_w, covM, covm, ratio_a;  // ratio_a: 1/sqrt(var ratio)
+    scdrs::DevBuf w_ptr, w_cursor, w_col, w_val;
+    scdrs::DevBuf dev_mat;   // float [n_cell x ld]: raw score minus the row reference; NaN = exact 0
+    scdrs::DevBuf row_ref;   // double [n_cell]
+    scdrs::DevBuf partial;   // double scratch for per-CTA column partials
+    scdrs::DevBuf colmean, col2, colmin;  // double [ncol]
+    scdrs::DevBuf row_mean, row_istd;     // double [n_cell]
+    scdrs::DevBuf scalars;                // double [8]: gmin, ...
+    scdrs::DevBuf query, mc_count, norm_mat;
+    int64_t n_cell_total = 0;
+    // pooled-null workspace
+    scdrs::DevBuf sort_keys[2], sort_idx[2], sort_tab, grid, hist, ge_sorted, ge_local, scan_tmp;
+    int32_t grid_bits = 0;  // number of grid cells
+    int sorted_buf = 0;     // which sort buffer holds the sorted queries
+    // single-GPU exchange buffers
+    scdrs::DevBuf x_colsum, x_col2, x_colmin, x_hist;
+    // staging
+    scdrs::DevBuf stage;
+};
+
+namespace scdrs {
+
+// ---- spmm_score.cu ------------------------------------------------------------------------
+int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                  const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                  const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio);
+int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
+                     const double* w);
+int spmm_score(scdrs_ctx* c);
+
+// ---- background.cu ------------------------------------------------------------------------
+int bg_colsum(scdrs_ctx* c, double* dev_colsum_out);
+int bg_rowstats(scdrs_ctx* c, const double* dev_colsum, int64_t n_cell_total, double* dev_col2,
+                double* dev_colmin);
+int bg_queries(scdrs_ctx* c, const double* dev_col2, const double* dev_colmin, float* dev_query);
+int bg_pack_dense(scdrs_ctx* c, int64_t n_cell, int32_t n_ctrl, const double* dev_vraw,
+                  const double* dev_mat, const double* dev_ratio);
+int bg_export_raw(scdrs_ctx* c, double* dev_raw_score, float* dev_ctrl_raw);
+
+// ---- empi_null.cu -------------------------------------------------------------------------
+int null_prepare_queries(scdrs_ctx* c, const float* dev_query_all, int64_t m);
+int null_count_pass(scdrs_ctx* c, unsigned long long* dev_hist, int64_t m, bool write_norm);
+int null_finish(scdrs_ctx* c, const unsigned long long* dev_hist_all, int64_t m, int64_t offset,
+                int64_t n_null_total, int64_t n_local, long long* dev_ge_out);
+int null_count_generic_f32(scdrs_ctx* c, int64_t n_t, const float* dev_t, int64_t n_null,
+                           const float* dev_null, long long* dev_ge);
+int null_count_generic_f64(scdrs_ctx* c, int64_t n_t, const double* dev_t, int64_t n_null,
+                           const double* dev_null, long long* dev_ge);
+
+// ---- stats.cu -----------------------------------------------------------------------------
+int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, double* dev_gsum,
+                    double* dev_gsumsq, double* dev_csum, double* dev_csumsq);
+
+// ---- scan (empi_null.cu) --------------------------------------------------------------------
+int exclusive_scan_u32(scdrs_ctx* c, const uint32_t* in, uint32_t* out, int64_t n);
+int exclusive_scan_u64(scdrs_ctx* c, const unsigned long long* in, unsigned long long* out,
+                       int64_t n);
+
+}  // namespace scdrs
+
+#define SCDRS_LAUNCH_CHECK(c)                      \
+    do {                                           \
+        (c)->launches++;                           \
+        SCDRS_CUDA(cudaGetLastError());            \
+    } while (0)

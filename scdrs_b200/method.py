@@ -1,0 +1,318 @@
+"""Host side of the scoring hot path: same functions, arguments, assertions and return types as
+``scdrs/method.py:12-632`` of the reference, with the arithmetic done by the sm_100a kernels in
+``libscdrs_b200.so`` (no CPU fallback).
+
+What stays on the host (Python/numpy/pandas, as in the reference): argument checks, the gene-list
+intersection, binning genes by ``ctrl_match_key`` and -- in compiled host code, bit-identical to
+numpy's legacy generator -- the control-gene draws; turning integer rank counts into p-values and
+z-scores; building the result DataFrame.
+"""
+import numpy as np
+import pandas as pd
+import scipy as sp
+import scipy.stats  # noqa: F401
+
+from . import _native
+from ._device import get_state
+
+_LEGAL_WEIGHT_OPT = {"uniform", "vs", "inv_std", "od"}
+
+
+# ----------------------------------------------------------------------------------------------
+# gene bins                                                              scdrs/method.py:283-297
+# ----------------------------------------------------------------------------------------------
+class _GeneBins:
+    """Genes grouped by ``ctrl_match_key`` in the order the reference visits them.
+
+    bin_ptr[n_bin + 1], bin_pos[...]: row positions of df_gene, bins in pandas-groupby order
+    (sorted labels, NaN dropped), genes inside a bin ordered by gene name
+    (``sorted(set_of_names)``, scdrs/method.py:296); code[n_gene]: bin of each gene or -1.
+    """
+
+    def __init__(self, df_gene, ctrl_match_key, n_genebin):
+        key = df_gene[ctrl_match_key]
+        names = (df_gene["gene"] if "gene" in df_gene else df_gene.index.to_series()).values
+        if key.unique().shape[0] < df_gene.shape[0] / 10:          # :284 categorical
+            labels = key.values
+        else:                                                        # :287-289 continuous
+            labels = pd.qcut(key, q=n_genebin, labels=False, duplicates="drop").values
+        code, uniq = pd.factorize(labels, sort=True)                 # sorted like groupby; NaN -> -1
+        name_rank = np.empty(len(names), dtype=np.int64)
+        name_rank[np.argsort(np.asarray(names, dtype=object), kind="stable")] = np.arange(len(names))
+        keep = np.flatnonzero(code >= 0)
+        order = keep[np.lexsort((name_rank[keep], code[keep]))]
+        self.code = code.astype(np.int64)
+        self.bin_pos = order.astype(np.int64)
+        counts = np.bincount(code[keep], minlength=len(uniq))
+        self.bin_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.n_bin = len(uniq)
+
+
+def _bins_for(df_gene, ctrl_match_key, n_genebin, cache=None):
+    if cache is None:
+        return _GeneBins(df_gene, ctrl_match_key, n_genebin)
+    h = pd.util.hash_pandas_object(df_gene[ctrl_match_key], index=True).values.sum()
+    ck = (ctrl_match_key, n_genebin, df_gene.shape[0], int(h))
+    if ck not in cache:
+        cache.clear()
+        cache[ck] = _GeneBins(df_gene, ctrl_match_key, n_genebin)
+    return cache[ck]
+
+
+def _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=None):
+    """Control sets as integer positions; see include/scdrs_b200.h:scdrs_select_ctrl.
+
+    trait_pos must be ordered by gene name.  Returns (ctrl_pos[n_ctrl, n_sc], ctrl_gw[n_sc]).
+    """
+    tcode = bins.code[trait_pos]
+    in_bin = tcode >= 0
+    ntrait = np.bincount(tcode[in_bin], minlength=bins.n_bin).astype(np.int32)
+    # the p-th control gene of a bin inherits the weight of the p-th trait gene (by name) of that bin
+    order = np.argsort(tcode[in_bin], kind="stable")
+    ctrl_gw = np.asarray(trait_gw, dtype=np.float64)[in_bin][order]
+    genes = bins.bin_pos if col_of is None else col_of[bins.bin_pos]
+    ctrl = _native.select_ctrl(random_seed, bins.bin_ptr, genes, ntrait, n_ctrl, int(ntrait.sum()))
+    return ctrl, ctrl_gw
+
+
+# ----------------------------------------------------------------------------------------------
+def score_cell(
+    data,
+    gene_list,
+    gene_weight=None,
+    ctrl_match_key="mean_var",
+    n_ctrl=1000,
+    n_genebin=200,
+    weight_opt="vs",
+    copy=False,
+    return_ctrl_raw_score=False,
+    return_ctrl_norm_score=False,
+    random_seed=0,
+    verbose=False,
+    save_intermediate=None,
+):
+    """Score cells based on the disease gene set (drop-in for ``scdrs.method.score_cell``,
+    scdrs/method.py:12-226; same parameters, same float32 DataFrame with columns
+    ``raw_score, norm_score, mc_pval, pval, nlog10_pval, zscore[, ctrl_raw_score_*][, ctrl_norm_score_*]``).
+
+    Differences from the reference, all outside the numerical contract: ``adata.X`` is NOT
+    converted to CSC in place (:98-99); the global numpy generator is re-seeded (:96) but not
+    advanced by the control draws; ``weight_opt="od"`` (benchmarking only, :352-355) and
+    ``save_intermediate`` text dumps are not part of the accelerated path and raise.
+    """
+    np.random.seed(random_seed)                                       # :96
+    adata = data.copy() if copy else data
+    n_cell, n_gene = adata.shape
+
+    assert (
+        "SCDRS_PARAM" in adata.uns
+    ), "adata.uns['SCDRS_PARAM'] not found, run `scdrs.pp.preprocess` first"
+    assert (
+        "GENE_STATS" in adata.uns["SCDRS_PARAM"]
+    ), "adata.uns['SCDRS_PARAM']['GENE_STATS'] not found, run `scdrs.pp.preprocess` first"
+    gene_stats_set_expect = {"mean", "var", "var_tech"}
+    gene_stats_set = set(adata.uns["SCDRS_PARAM"]["GENE_STATS"])
+    assert (
+        len(gene_stats_set_expect - gene_stats_set) == 0
+    ), "One of 'mean', 'var', 'var_tech' not found in adata.uns['SCDRS_PARAM']['GENE_STATS'], run `scdrs.pp.preprocess` first"
+    assert ctrl_match_key in adata.uns["SCDRS_PARAM"]["GENE_STATS"], (
+        "ctrl_match_key=%s not found in adata.uns['SCDRS_PARAM']['GENE_STATS']" % ctrl_match_key
+    )
+    assert weight_opt in _LEGAL_WEIGHT_OPT, (
+        "weight_opt=%s is not one of {'uniform', 'vs', 'inv_std', 'od}'" % weight_opt
+    )
+    if weight_opt == "od":
+        raise NotImplementedError("weight_opt='od' (benchmarking-only overdispersion score) is outside the B200 hot path")
+    if save_intermediate is not None:
+        raise NotImplementedError("save_intermediate text dumps are not supported by the B200 path")
+
+    if verbose:
+        msg = "# scdrs.method.score_cell summary:"
+        msg += "\n    n_cell=%d, n_gene=%d," % (n_cell, n_gene)
+        msg += "\n    n_disease_gene=%d," % len(gene_list)
+        msg += "\n    n_ctrl=%d, n_genebin=%d," % (n_ctrl, n_genebin)
+        msg += "\n    ctrl_match_key='%s'," % ctrl_match_key
+        msg += "\n    weight_opt='%s'," % weight_opt
+        msg += "\n    return_ctrl_raw_score=%s," % return_ctrl_raw_score
+        msg += "\n    return_ctrl_norm_score=%s," % return_ctrl_norm_score
+        msg += "\n    random_seed=%d, verbose=%s," % (random_seed, verbose)
+        msg += "\n    save_intermediate=%s," % save_intermediate
+        print(msg)
+
+    param = adata.uns["SCDRS_PARAM"]
+    implicit = bool(param["FLAG_SPARSE"] and param["FLAG_COV"])
+    state = get_state(adata)
+    prep = _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed)
+    if verbose:
+        print("# scdrs.method.score_cell: use %d overlapping genes for scoring" % len(prep["genes"]))
+
+    ctx = state.ensure_matrix(adata)
+    state.ensure_cov(adata, implicit)
+    ctx.set_gene_stats(prep["var"], prep["var_tech"])
+    use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))  # :187
+    out = ctx.score_trait(
+        prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"], weight_opt, use_ratio,
+        want_ctrl_raw=return_ctrl_raw_score, want_ctrl_norm=return_ctrl_norm_score,
+    )
+    return _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score)
+
+
+def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed):
+    """Host work of one trait: gene intersection (:146-159) and control draws (:168)."""
+    param = adata.uns["SCDRS_PARAM"]
+    cache = state.bins_cache if state is not None else None
+    ck = ("df_gene", id(param["GENE_STATS"]), id(adata.var_names), param["GENE_STATS"].shape)
+    if cache is not None and ck in cache:
+        df_gene, col_of = cache[ck]
+    else:
+        df_gene = param["GENE_STATS"].loc[adata.var_names].copy()       # :146
+        df_gene["gene"] = df_gene.index
+        df_gene.drop_duplicates(subset="gene", inplace=True)            # :148
+        col_of = pd.Index(adata.var_names).get_indexer(df_gene["gene"].values).astype(np.int64)
+        if cache is not None:
+            for k_ in [k_ for k_ in cache if isinstance(k_, tuple) and k_[0] == "df_gene"]:
+                del cache[k_]
+            cache[ck] = (df_gene, col_of)
+
+    gene_list = list(gene_list)
+    gene_weight = list(gene_weight) if gene_weight is not None else [1] * len(gene_list)
+    dic_gene_weight = {x: y for x, y in zip(gene_list, gene_weight)}    # :157
+    pos_index = pd.Index(df_gene["gene"].values)
+    genes = sorted(set(gene_list) & set(pos_index))                     # :158
+    trait_pos = pos_index.get_indexer(genes).astype(np.int64)
+    trait_gw = np.array([dic_gene_weight[x] for x in genes], dtype=np.float64)
+
+    bins = _bins_for(df_gene, ctrl_match_key, n_genebin, cache)
+    ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=col_of)
+
+    # gene statistics aligned to the columns of X
+    n_gene = adata.shape[1]
+    var = np.zeros(n_gene)
+    var_tech = np.zeros(n_gene)
+    var[col_of] = df_gene["var"].values.astype(np.float64)
+    var_tech[col_of] = df_gene["var_tech"].values.astype(np.float64)
+    return dict(genes=genes, trait_cols=col_of[trait_pos].astype(np.int32), trait_gw=trait_gw,
+                ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=var, var_tech=var_tech)
+
+
+def _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score):
+    """Integer counts -> p-values / z-scores -> float32 DataFrame (:205-226)."""
+    n_cell = adata.shape[0]
+    n_null = out.get("n_null_total", n_cell * n_ctrl)
+    mc_p = (1 + out["mc_count"].astype(np.float64)) / (1 + n_ctrl)            # :205
+    pooled_p = (out["ge_count"].astype(np.float64) + 1) / (n_null + 1)        # :631
+    with np.errstate(divide="ignore"):
+        nlog10_pooled_p = -np.log10(pooled_p)                                 # :207
+    pooled_z = -sp.stats.norm.ppf(pooled_p).clip(min=-10, max=10)             # :208
+    dic_res = {
+        "raw_score": out["raw_score"],
+        "norm_score": out["norm_score"],
+        "mc_pval": mc_p,
+        "pval": pooled_p,
+        "nlog10_pval": nlog10_pooled_p,
+        "zscore": pooled_z,
+    }
+    df_res = pd.DataFrame(index=adata.obs.index, data=dic_res, dtype=np.float32)
+    blocks = [df_res]
+    if return_ctrl_raw_score:
+        blocks.append(pd.DataFrame(out["ctrl_raw"], index=adata.obs.index,
+                                   columns=["ctrl_raw_score_%d" % i for i in range(n_ctrl)]))
+    if return_ctrl_norm_score:
+        blocks.append(pd.DataFrame(out["ctrl_norm"], index=adata.obs.index,
+                                   columns=["ctrl_norm_score_%d" % i for i in range(n_ctrl)]))
+    if len(blocks) > 1:
+        df_res = pd.concat(blocks, axis=1)
+    return df_res
+
+
+# ----------------------------------------------------------------------------------------------
+def _select_ctrl_geneset(input_df_gene, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed):
+    """Matched control gene sets (drop-in for scdrs/method.py:229-309).
+
+    Returns (dic_ctrl_list, dic_ctrl_weight): control set index -> list of gene names / weights.
+    Bit-identical to the reference's numpy draws.
+    """
+    np.random.seed(random_seed)                                           # :276
+    df_gene = input_df_gene.copy()
+    if "gene" not in df_gene:
+        df_gene["gene"] = df_gene.index
+    names = df_gene["gene"].values
+    dic_gene_weight = {x: y for x, y in zip(gene_list, gene_weight)}
+    pos_index = pd.Index(names)
+    genes = sorted(set(gene_list) & set(names))
+    trait_pos = pos_index.get_indexer(genes).astype(np.int64)
+    trait_gw = np.array([dic_gene_weight[x] for x in genes], dtype=np.float64)
+    bins = _GeneBins(df_gene, ctrl_match_key, n_genebin)
+    ctrl_pos, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed)
+    # weights come back as the caller's own objects, like the reference's lists
+    w_list = [dic_gene_weight[genes[i]] for i in
+              np.flatnonzero(bins.code[trait_pos] >= 0)[np.argsort(bins.code[trait_pos][bins.code[trait_pos] >= 0], kind="stable")]]
+    dic_ctrl_list = {i: list(names[ctrl_pos[i]]) for i in range(n_ctrl)}
+    dic_ctrl_weight = {i: list(w_list) for i in range(n_ctrl)}
+    return dic_ctrl_list, dic_ctrl_weight
+
+
+def _compute_raw_score(adata, gene_list, gene_weight, weight_opt):
+    """Raw score of one gene set (drop-in for scdrs/method.py:312-402).
+
+    Returns (v_raw_score[n_cell] float64, v_score_weight[n_gene_in_list] float64).
+    """
+    gene_list = list(gene_list)
+    gene_weight = list(gene_weight)
+    assert weight_opt in _LEGAL_WEIGHT_OPT, (
+        "weight_opt=%s is not one of {'uniform', 'vs', 'inv_std', 'od}'" % weight_opt
+    )
+    if weight_opt == "od":
+        raise NotImplementedError("weight_opt='od' (benchmarking-only overdispersion score) is outside the B200 hot path")
+    assert (
+        "SCDRS_PARAM" in adata.uns
+    ), "adata.uns['SCDRS_PARAM'] not found, run `scdrs.pp.preprocess` first"
+    param = adata.uns["SCDRS_PARAM"]
+    df_gene = param["GENE_STATS"]
+    if weight_opt == "uniform":
+        v_score_weight = np.ones(len(gene_list))
+    if weight_opt == "vs":
+        v_score_weight = 1 / np.sqrt(df_gene.loc[gene_list, "var_tech"].values.astype(np.float64) + 1e-2)
+    if weight_opt == "inv_std":
+        v_score_weight = 1 / np.sqrt(df_gene.loc[gene_list, "var"].values.astype(np.float64) + 1e-2)
+    if gene_weight is not None:
+        v_score_weight = v_score_weight * np.array(gene_weight)
+    v_score_weight = v_score_weight / v_score_weight.sum()
+
+    gene_idx = adata.var_names.get_indexer(gene_list)
+    keep = gene_idx >= 0
+    state = get_state(adata)
+    ctx = state.ensure_matrix(adata)
+    state.ensure_cov(adata, bool(param["FLAG_SPARSE"] and param["FLAG_COV"]))
+    v_raw_score = ctx.compute_raw_score(gene_idx[keep], v_score_weight[keep])[:, 0]
+    return v_raw_score, v_score_weight
+
+
+def _correct_background(v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t, save_intermediate=None):
+    """Cell-wise and gene-set-wise background correction (drop-in for scdrs/method.py:482-598).
+
+    The device computes in float64 and stores float32, so results carry float32 resolution.
+    """
+    if save_intermediate is not None:
+        raise NotImplementedError("save_intermediate text dumps are not supported by the B200 path")
+    return _scratch_context().correct_background(v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t)
+
+
+def _get_p_from_empi_null(v_t, v_t_null):
+    """p = (1 + #{null >= t}) / (1 + N) (drop-in for scdrs/method.py:601-632); exact counts."""
+    v_t = np.array(v_t)
+    v_t_null = np.array(v_t_null)
+    ge = _scratch_context().empi_null_count(v_t, v_t_null)
+    return (ge.astype(np.float64) + 1) / (v_t_null.shape[0] + 1)
+
+
+_SCRATCH = {}
+
+
+def _scratch_context():
+    from ._device import _DEFAULT_DEVICE
+
+    dev = _DEFAULT_DEVICE[0]
+    if dev not in _SCRATCH:
+        _SCRATCH[dev] = _native.Context(dev)
+    return _SCRATCH[dev]

@@ -1,0 +1,155 @@
+"""I/O glue on either side of the hot path: same behaviour as the loaders in ``scdrs/util.py`` of
+the reference (``load_h5ad :46-92``, ``load_gs :194-274``, ``load_homolog_mapping :152-191``,
+``save_gs :277-308``).  ``anndata`` / ``scanpy`` are absent from this image, so reading goes through
+``anndata_lite`` and the scanpy preprocessing steps are restated on scipy.sparse."""
+import os
+from typing import Dict, List
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+from .anndata_lite import AnnData, read_h5ad
+
+
+def convert_species_name(species):
+    if species in ["Mouse", "mouse", "Mus_musculus", "mus_musculus", "mmusculus"]:
+        return "mmusculus"
+    if species in ["Human", "human", "Homo_sapiens", "homo_sapiens", "hsapiens"]:
+        return "hsapiens"
+    raise ValueError("species name '%s' is not supported" % species)
+
+
+def str_or_list_like(x):
+    """'str', 'list_like' or 'others' by duck typing (scdrs/util.py:26-43)."""
+    if hasattr(x, "strip"):
+        return "str"
+    if hasattr(x, "__getitem__") or hasattr(x, "__iter__"):
+        return "list_like"
+    return "others"
+
+
+def _nnz_per_row(X):
+    return np.diff(X.indptr) if sparse.issparse(X) else (X != 0).sum(axis=1)
+
+
+def load_h5ad(h5ad_file, flag_filter_data=False, flag_raw_count=True, min_genes=250, min_cells=50):
+    """Load an h5ad file, check it, optionally filter and normalise it (scdrs/util.py:46-92).
+
+    The scanpy calls of the reference are restated: ``filter_cells(min_genes)`` keeps cells with
+    at least ``min_genes`` expressed genes (adds ``obs["n_genes"]``); ``filter_genes(min_cells)``
+    keeps genes expressed in at least ``min_cells`` cells (adds ``var["n_cells"]``);
+    ``normalize_per_cell(counts_per_cell_after=1e4)`` drops cells with fewer than 1 count, stores
+    ``obs["n_counts"]`` and scales each cell to 1e4 counts; ``log1p`` is the natural log.
+    """
+    adata = read_h5ad(h5ad_file)
+    if np.isnan(adata.X.sum()):
+        raise ValueError(
+            "h5ad expression matrix should not contain NaN. Please impute them beforehand."
+        )
+    if (adata.X < 0).sum() > 0:
+        raise ValueError(
+            "h5ad expression matrix should not contain negative values. "
+            "This is because in the preprocessing step, "
+            "scDRS models the gene-level log mean-variance relationship. "
+            "See scdrs.pp.compute_stats for details."
+        )
+    if flag_filter_data:
+        X = sparse.csr_matrix(adata.X) if sparse.issparse(adata.X) else adata.X
+        n_genes = np.asarray(_nnz_per_row(X)).reshape(-1)
+        keep = n_genes >= min_genes
+        adata = adata[keep, :]
+        adata.obs["n_genes"] = n_genes[keep]
+        Xc = sparse.csc_matrix(adata.X) if sparse.issparse(adata.X) else adata.X
+        n_cells = np.diff(Xc.indptr) if sparse.issparse(Xc) else (Xc != 0).sum(axis=0)
+        n_cells = np.asarray(n_cells).reshape(-1)
+        keepg = n_cells >= min_cells
+        adata = adata[:, keepg]
+        adata.var["n_cells"] = n_cells[keepg]
+    if flag_raw_count:
+        counts = np.asarray(adata.X.sum(axis=1)).reshape(-1)
+        keep = counts >= 1
+        if not keep.all():
+            adata = adata[keep, :]
+            counts = counts[keep]
+        adata.obs["n_counts"] = counts
+        scale = 1e4 / counts
+        if sparse.issparse(adata.X):
+            X = sparse.csr_matrix(adata.X, dtype=np.float32, copy=True)
+            X.data *= np.repeat(scale, np.diff(X.indptr)).astype(np.float32)
+            X.data = np.log1p(X.data)
+        else:
+            X = np.log1p(np.asarray(adata.X, dtype=np.float32) * scale[:, None].astype(np.float32))
+        adata = AnnData(X, adata.obs, adata.var, adata.uns)
+    return adata
+
+
+def load_homolog_mapping(src_species: str, dst_species: str) -> dict:
+    """Mouse <-> human gene symbol homologs (scdrs/util.py:152-191)."""
+    src_species = convert_species_name(src_species)
+    dst_species = convert_species_name(dst_species)
+    assert src_species != dst_species, "src and dst cannot be the same"
+    df_hom = pd.read_csv(
+        os.path.join(os.path.dirname(__file__), "data/mouse_human_homologs.txt"), sep="\t"
+    )
+    if (src_species == "hsapiens") & (dst_species == "mmusculus"):
+        return dict(zip(df_hom["HUMAN_GENE_SYM"], df_hom["MOUSE_GENE_SYM"]))
+    if (src_species == "mmusculus") & (dst_species == "hsapiens"):
+        return dict(zip(df_hom["MOUSE_GENE_SYM"], df_hom["HUMAN_GENE_SYM"]))
+    raise NotImplementedError(f"gene conversion from {src_species} to {dst_species} is not supported")
+
+
+def load_gs(gs_path: str, src_species: str = None, dst_species: str = None,
+            to_intersect: List[str] = None) -> dict:
+    """Parse a ``.gs`` file into ``{trait: (gene_list, gene_weight_list)}`` (scdrs/util.py:194-274):
+    ``g1,g2`` (weights 1.0) or ``g1:w1,g2:w2``; later duplicates win; optional homolog mapping and
+    intersection with ``to_intersect``; file order preserved."""
+    assert (src_species is None) == (
+        dst_species is None
+    ), "src_species and dst_species must be both None or not None"
+    dict_map = None
+    if (src_species is not None) and (dst_species is not None) and (src_species != dst_species):
+        dict_map = load_homolog_mapping(src_species, dst_species)
+    keep = set(to_intersect) if to_intersect is not None else None
+    dict_gs = {}
+    df_gs = pd.read_csv(gs_path, sep="\t")
+    for trait, gs in zip(df_gs.iloc[:, 0], df_gs.iloc[:, 1]):
+        fields = [g.split(":") for g in gs.split(",")]
+        if all(len(g) == 1 for g in fields):
+            weights = {g[0]: 1.0 for g in fields}
+        elif all(len(g) == 2 for g in fields):
+            weights = {g[0]: float(g[1]) for g in fields}
+        else:
+            raise ValueError(f"gene set {trait} contains genes with invalid format")
+        if dict_map is not None:
+            weights = {dict_map[g]: w for g, w in weights.items() if g in dict_map}
+        if keep is not None:
+            weights = {g: w for g, w in weights.items() if g in keep}
+        genes = list(weights.keys())
+        dict_gs[trait] = (genes, [weights[g] for g in genes])
+    return dict_gs
+
+
+def save_gs(gs_path: str, dict_gs: dict) -> None:
+    """Write a ``.gs`` file (scdrs/util.py:277-308)."""
+    rows: Dict = {"TRAIT": [], "GENESET": []}
+    for trait, val in dict_gs.items():
+        rows["TRAIT"].append(trait)
+        if isinstance(val, tuple):
+            rows["GENESET"].append(",".join([g + ":" + str(w) for g, w in zip(*val)]))
+        else:
+            rows["GENESET"].append(",".join(val))
+    pd.DataFrame(rows).to_csv(gs_path, sep="\t", index=False)
+
+
+def fdr_bh(pvals):
+    """Benjamini-Hochberg adjusted p-values (what ``multipletests(method='fdr_bh')[1]`` returns;
+    used only for the per-trait log line of the CLI, bin/scdrs:289-303)."""
+    p = np.asarray(pvals, dtype=np.float64)
+    n = p.shape[0]
+    order = np.argsort(p)
+    adj = p[order] * n / np.arange(1, n + 1)
+    adj = np.minimum.accumulate(adj[::-1])[::-1]
+    out = np.empty(n)
+    out[order] = np.minimum(adj, 1.0)
+    return out

@@ -1,0 +1,275 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the reference's golden
+vectors.  Integer outputs (control indices, rank counts) must be bit-exact; floating-point outputs
+must agree within 1e-5 (BASELINE.json north_star), tolerance written in each test."""
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import sparse
+
+import helpers
+from oracle import scdrs_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5     # north_star: raw, normalised and z-scores within 1e-5 relative in fp32
+ATOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def sc(native_lib):
+    import scdrs_b200
+
+    return scdrs_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(native_lib):
+    from scdrs_b200 import _native
+
+    c = _native.Context(0)
+    yield c
+    c.close()
+
+
+def _check_counts_self_consistent(df, n_ctrl):
+    """mc / pooled counts must be EXACTLY what numpy gets from the returned float32 scores."""
+    norm = df["norm_score"].values
+    ctrl = df[["ctrl_norm_score_%d" % i for i in range(n_ctrl)]].values
+    mc = (ctrl >= norm[:, None]).sum(axis=1)
+    assert np.array_equal(df["mc_pval"].values, ((1 + mc) / (1 + n_ctrl)).astype(np.float32))
+    ge = orc.null_ge_count(norm, ctrl.reshape(-1))
+    p = ((ge + 1) / (ctrl.size + 1)).astype(np.float32)
+    assert np.array_equal(df["pval"].values, p)
+
+
+def _compare_with_reference(df, ref, n_ctrl, n_cell):
+    """Float columns within tolerance; p-value columns equal except where ties straddle it."""
+    for c in ["raw_score", "norm_score"]:
+        assert np.allclose(df[c].values, ref[c].values, rtol=RTOL, atol=ATOL), c
+    cr = ["ctrl_raw_score_%d" % i for i in range(n_ctrl)]
+    cn = ["ctrl_norm_score_%d" % i for i in range(n_ctrl)]
+    if cr[0] in ref and cr[0] in df:
+        assert np.allclose(df[cr].values, ref[cr].values, rtol=RTOL, atol=ATOL)
+    if cn[0] in ref and cn[0] in df:
+        assert np.allclose(df[cn].values, ref[cn].values, rtol=RTOL, atol=ATOL)
+    n_null = n_cell * n_ctrl
+    # rank counts: a difference needs a null value within the tolerance of the trait score
+    d_rank = np.abs(np.round(df["pval"].values.astype(np.float64) * (n_null + 1)) -
+                    np.round(ref["pval"].values.astype(np.float64) * (n_null + 1)))
+    n_diff = int((d_rank > 0).sum())
+    assert d_rank.max() <= 2 and n_diff <= max(1, n_cell // 100), (n_diff, d_rank.max())
+    d_mc = np.abs(df["mc_pval"].values - ref["mc_pval"].values) * (1 + n_ctrl)
+    assert d_mc.max() <= 1.01 and (d_mc > 0.5).sum() <= max(1, n_cell // 100)
+    ok = d_rank == 0
+    assert np.allclose(df["zscore"].values[ok], ref["zscore"].values[ok], rtol=RTOL, atol=ATOL)
+    assert np.allclose(df["nlog10_pval"].values[ok], ref["nlog10_pval"].values[ok], rtol=RTOL, atol=ATOL)
+    return n_diff
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases())
+def test_score_cell_matches_reference_golden_outputs(sc, path):
+    adata, cov, case = helpers.load_case(path)
+    df = sc.score_cell(adata, case["gene_list"], gene_weight=case["gene_weight"],
+                       ctrl_match_key=case["ctrl_match_key"], n_ctrl=case["n_ctrl"],
+                       weight_opt=case["weight_opt"], return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+    ref = case["ref"]
+    assert list(df.columns) == list(ref.columns) and df.values.dtype == np.float32
+    assert list(df.index) == list(ref.index)
+    _check_counts_self_consistent(df, case["n_ctrl"])
+    _compare_with_reference(df, ref, case["n_ctrl"], adata.shape[0])
+
+
+@pytest.mark.parametrize("cov", [False, True])
+@pytest.mark.parametrize("dense", [False, True])
+def test_score_cell_toy_data_golden_files(sc, cov, dense):
+    """The reference's own integration tests (tests/test_method_score_cell_main.py:82-177)."""
+    adata, df_cov, df_gs, ref, stats = helpers.load_toy()
+    genes = df_gs.loc["toydata_gs_mouse", "GENESET"].split(",")
+    genes = sorted(set(genes) & set(adata.var_names))
+    if dense:
+        adata.X = adata.X.toarray()
+    sc.preprocess(adata, cov=df_cov if cov else None, n_mean_bin=20, n_var_bin=20, copy=False)
+    key = "cov" if cov else "nocov"
+    adata.uns["SCDRS_PARAM"]["GENE_STATS"]["mean_var"] = stats[key]["mean_var"]
+    df = sc.score_cell(adata, genes, ctrl_match_key="mean_var", n_ctrl=20, weight_opt="vs",
+                       return_ctrl_norm_score=True)
+    gold = ref["REF_COV" if cov else "REF_NOCOV"]
+    for c in ["raw_score", "norm_score", "mc_pval", "pval"]:
+        assert np.allclose(df[c].values, gold[c].values, rtol=1e-2, equal_nan=True), c   # the reference's bar
+    # and the tight bar: the golden files carry 8 significant digits
+    for c in ["raw_score", "norm_score", "mc_pval", "pval", "nlog10_pval", "zscore"]:
+        assert np.allclose(df[c].values, gold[c].values, rtol=5e-5, atol=5e-5), c
+    if cov:
+        cols = ["ctrl_norm_score_%d" % i for i in range(20)]
+        assert np.allclose(df[cols].values, ref["REF_COV_FULL"][cols].values, rtol=5e-5, atol=5e-5)
+    _check_counts_self_consistent(df, 20)
+
+
+@pytest.mark.parametrize("use_cov,weighted,key,wopt,n_ctrl", [
+    (True, False, "mean_var", "vs", 100),
+    (False, True, "mean_var", "vs", 64),
+    (True, True, "mean", "inv_std", 33),
+    (False, False, "mean_var", "uniform", 1),
+])
+def test_score_cell_matches_oracle_on_synthetic(sc, use_cov, weighted, key, wopt, n_ctrl):
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(1500, 3000, density=0.1, seed=31)
+    orc.preprocess(adata, cov=cov if use_cov else None, loess_impl=loess)
+    genes, w = synth.make_traits(adata.var_names, 1, 200, weighted=weighted, seed=77)["trait_00"]
+    ref, info = orc.score_cell(adata, genes, gene_weight=w, ctrl_match_key=key, n_ctrl=n_ctrl, weight_opt=wopt,
+                               return_ctrl_raw_score=True, return_ctrl_norm_score=True, return_internals=True)
+    df = sc.score_cell(adata, genes, gene_weight=w, ctrl_match_key=key, n_ctrl=n_ctrl, weight_opt=wopt,
+                       return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+    _check_counts_self_consistent(df, n_ctrl)
+    _compare_with_reference(df, ref, n_ctrl, adata.shape[0])
+
+
+def test_score_cell_zero_rows_get_the_minimum(sc):
+    """Cells whose raw score is exactly 0 (scdrs/method.py:521-523, 581-583), plus empty rows."""
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, _ = synth.make_adata(400, 1500, density=0.08, seed=5)
+    X = adata.X.tolil()
+    X[3, :] = 0
+    X[17, :] = 0
+    adata.X = sparse.csr_matrix(X.tocsr())
+    adata.X.eliminate_zeros()
+    orc.preprocess(adata, cov=None, loess_impl=loess)
+    genes, w = synth.make_traits(adata.var_names, 1, 40, seed=3)["trait_00"]
+    ref = orc.score_cell(adata, genes, n_ctrl=25, return_ctrl_norm_score=True, return_ctrl_raw_score=True)
+    df = sc.score_cell(adata, genes, n_ctrl=25, return_ctrl_norm_score=True, return_ctrl_raw_score=True)
+    assert df["raw_score"].iloc[3] == 0 and df["raw_score"].iloc[17] == 0
+    assert (ref["raw_score"] == 0).sum() >= 2
+    _check_counts_self_consistent(df, 25)
+    _compare_with_reference(df, ref, 25, 400)
+    assert df["norm_score"].iloc[3] == df["norm_score"].min()
+
+
+def test_compute_raw_score_matches_numpy(sc):
+    """_compute_raw_score for sparse x cov x weight options (tests/test_method_score_cell_other.py:64-281)."""
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    for use_cov in (False, True):
+        adata, cov = synth.make_adata(300, 800, density=0.2, seed=9)
+        orc.preprocess(adata, cov=cov if use_cov else None, loess_impl=loess)
+        param = adata.uns["SCDRS_PARAM"]
+        genes = list(adata.var_names[[5, 17, 200, 301, 644]])
+        gw = [1.0, 2.0, 0.5, 3.0, 1.5]
+        for wopt in ("uniform", "vs", "inv_std"):
+            v_raw, v_w = sc.method._compute_raw_score(adata, genes, gw, wopt)
+            idx = adata.var_names.get_indexer(genes)
+            w = orc.score_weights(param["GENE_STATS"], idx, gw, wopt)
+            kw = {}
+            if use_cov:
+                kw = dict(cov_mat=param["COV_MAT"].values, cov_beta=param["COV_BETA"].values,
+                          gene_mean=param["COV_GENE_MEAN"].values)
+            want = orc.compute_raw_score(adata.X.tocsc(), idx, w, **kw)
+            assert np.allclose(v_w, w, rtol=1e-12)
+            assert np.allclose(v_raw, want, rtol=1e-6, atol=1e-7), (use_cov, wopt)
+
+
+def test_correct_background_finds_planted_cell(sc):
+    """_correct_background under perturbations (tests/test_method_score_cell_other.py:390-446)."""
+    rng = np.random.default_rng(0)
+    n_cell, n_ctrl = 200, 100
+    for config in range(5):
+        v_raw = rng.normal(size=n_cell) * 0.1 + 5
+        mat = rng.normal(size=(n_cell, n_ctrl)) * 0.1 + 5
+        v_raw[5] += 1.0
+        ratio = np.ones(n_ctrl)
+        if config == 1:
+            mat = mat + rng.normal(size=n_ctrl)              # gene-set-wise shifts
+        if config == 2:
+            v_raw += np.linspace(0, 3, n_cell); mat += np.linspace(0, 3, n_cell)[:, None]   # cell-wise shifts
+        if config == 3:
+            ratio = rng.uniform(0.5, 2, size=n_ctrl); mat = 5 + (mat - 5) * np.sqrt(ratio)
+        if config == 4:
+            v_raw[10:20] = 0; mat[10:20, ::3] = 0            # zero masking
+        got_t, got_c = sc.method._correct_background(v_raw, mat, ratio)
+        want_t, want_c = orc.correct_background(v_raw, mat, ratio)
+        assert got_t[5] > 3
+        assert np.allclose(got_t, want_t, rtol=RTOL, atol=ATOL), config
+        assert np.allclose(got_c, want_c, rtol=RTOL, atol=ATOL), config
+
+
+def test_get_p_from_empi_null_known_answer_and_exact_counts(sc, ctx):
+    # tests/test_method_score_cell_other.py:449-458
+    assert np.allclose(sc.method._get_p_from_empi_null([0, 1], [0.5, 0.6, 0.7]), [1, 0.25])
+    rng = np.random.default_rng(1)
+    for dt in (np.float32, np.float64):
+        for n_t, n_null in [(1, 1), (7, 0), (1000, 100000), (4097, 300001)]:
+            t = rng.normal(size=n_t).astype(dt)
+            null = rng.normal(size=n_null).astype(dt)
+            if n_null > 10:
+                null[:5] = t[0]                      # exact ties count as >=
+                null[5:9] = [np.inf, -np.inf, 0.0, -0.0]
+                t[-1] = 0.0
+            got = ctx.empi_null_count(t, null)
+            assert np.array_equal(got, orc.null_ge_count(t, null)), (dt, n_t, n_null)
+    # heavy duplication and a constant query vector
+    t = np.repeat(np.float32([0.5, -1.0, 0.5]), 400)
+    null = np.round(rng.normal(size=50000), 1).astype(np.float32)
+    assert np.array_equal(ctx.empi_null_count(t, null), orc.null_ge_count(t, null))
+    t = np.full(300, 2.0, np.float32)
+    assert np.array_equal(ctx.empi_null_count(t, null), orc.null_ge_count(t, null))
+
+
+def test_full_size_properties(sc, ctx):
+    """Size-independent properties at a larger shape: linearity of the raw score in the weights,
+    rank counts consistent with the returned scores, idempotence of a repeated call."""
+    from scdrs_b200 import synth
+
+    X = synth.make_csr(20000, 5000, density=0.1, seed=2)
+    ctx.set_csr_host(X.indptr, X.indices, X.data, X.shape[1])
+    rng = np.random.default_rng(4)
+    genes = np.stack([rng.choice(5000, size=300, replace=False) for _ in range(3)]).astype(np.int32)
+    genes[2] = genes[0]
+    w = rng.uniform(0.1, 1, size=(3, 300))
+    w[2] = 2.0 * w[0]
+    raw = ctx.compute_raw_score(genes, w)
+    assert np.allclose(raw[:, 2], 2.0 * raw[:, 0], rtol=1e-6, atol=1e-9)                  # linearity
+    want = np.asarray(X[:, genes[1]] @ w[1]).reshape(-1)
+    assert np.allclose(raw[:, 1], want, rtol=1e-6, atol=1e-7)
+    raw2 = ctx.compute_raw_score(genes, w)
+    assert np.array_equal(raw, raw2)                                                      # bitwise reproducible
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases())
+def test_preprocess_matches_reference_golden_stats(sc, path):
+    adata, cov, case = helpers.load_case(path, with_param=False)
+    sc.preprocess(adata, cov=cov if case["use_cov"] else None, adj_prop=case["adj_prop"])
+    param, z = adata.uns["SCDRS_PARAM"], case["z"]
+    assert set(param) >= {"FLAG_SPARSE", "FLAG_COV", "FLAG_ADJ_PROP", "GENE_STATS", "CELL_STATS"}
+    assert list(param["GENE_STATS"].columns) == ["mean", "var", "var_tech", "ct_mean", "ct_var", "ct_var_tech", "mean_var"]
+    gs = param["GENE_STATS"]
+    tol = 1e-7 if case["use_cov"] else 2e-5      # reference normal sparse mode accumulates in float32
+    for c in ["mean", "var", "ct_mean", "ct_var", "var_tech", "ct_var_tech"]:
+        assert np.allclose(gs[c].values.astype(float), z["gs_" + c], rtol=max(tol, 1e-5 if "tech" in c else tol), atol=1e-10), c
+    n_bin_diff = int((gs["mean_var"].astype(str).values != z["gs_mean_var"]).sum())
+    assert n_bin_diff <= (0 if case["use_cov"] else 5), n_bin_diff
+    assert np.allclose(param["CELL_STATS"]["mean"].values.astype(float), z["cs_mean"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(param["CELL_STATS"]["var"].values.astype(float), z["cs_var"], rtol=1e-4, atol=1e-9)
+    if case["use_cov"]:
+        assert np.allclose(param["COV_BETA"].values, z["cov_beta"], rtol=1e-9, atol=1e-12)
+
+
+def test_compute_stats_modes_agree(sc):
+    """sparse + cov must equal dense + cov (tests/test_pp.py:115-161 of the reference)."""
+    from scdrs_b200 import synth
+
+    a_sp, cov = synth.make_adata(500, 1000, density=0.15, seed=8)
+    a_dn = a_sp.copy()
+    a_dn.X = a_dn.X.toarray()
+    sc.preprocess(a_sp, cov=cov)
+    sc.preprocess(a_dn, cov=cov)
+    assert a_sp.uns["SCDRS_PARAM"]["FLAG_SPARSE"] and not a_dn.uns["SCDRS_PARAM"]["FLAG_SPARSE"]
+    g1, g2 = a_sp.uns["SCDRS_PARAM"]["GENE_STATS"], a_dn.uns["SCDRS_PARAM"]["GENE_STATS"]
+    for c in ["mean", "var", "ct_mean", "ct_var"]:
+        assert np.allclose(g1[c].values.astype(float), g2[c].values.astype(float), rtol=1e-4, atol=1e-6), c
+    c1, c2 = a_sp.uns["SCDRS_PARAM"]["CELL_STATS"], a_dn.uns["SCDRS_PARAM"]["CELL_STATS"]
+    assert np.allclose(c1["mean"].values.astype(float), c2["mean"].values.astype(float), rtol=1e-4, atol=1e-6)
+    assert np.allclose(c1["var"].values.astype(float), c2["var"].values.astype(float), rtol=1e-3, atol=1e-6)

@@ -1,0 +1,172 @@
+"""CPU tests of the host logic and of the C-ABI library surface (no kernel launches)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import helpers
+from oracle import scdrs_oracle as orc
+from scdrs_b200 import _native, method, util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    header = open(os.path.join(ROOT, "include", "scdrs_b200.h")).read()
+    declared = set(re.findall(r"\b(scdrs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(native_lib, name), name
+    assert native_lib.scdrs_abi_version() == 1
+
+
+def test_context_creation_fails_loudly_without_gpu(native_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback|failed"):
+        _native.Context(0)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 12345, 2 ** 32 - 1])
+def test_select_ctrl_draws_equal_numpy_legacy_generator(native_lib, seed):
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1, 90, size=120)
+    bin_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    bin_genes = rng.permutation(bin_ptr[-1]).astype(np.int32)
+    ntrait = np.minimum(rng.integers(0, 4, size=120), sizes).astype(np.int32)
+    n_ctrl, n_s = 50, int(ntrait.sum())
+    got = _native.select_ctrl(seed, bin_ptr, bin_genes, ntrait, n_ctrl, n_s)
+    rs = np.random.RandomState(seed)
+    want = [[] for _ in range(n_ctrl)]
+    for b in range(120):
+        if ntrait[b] == 0:
+            continue
+        g = bin_genes[bin_ptr[b]:bin_ptr[b + 1]]
+        for i in range(n_ctrl):
+            want[i].extend(g[rs.permutation(len(g))[: ntrait[b]]])
+    assert np.array_equal(got, np.array(want))
+
+
+def test_select_ctrl_equals_np_random_choice_on_strings(native_lib):
+    names = sorted("g%03d" % i for i in range(57))
+    np.random.seed(7)
+    want = [list(np.random.choice(names, size=5, replace=False)) for _ in range(3)]
+    got = _native.select_ctrl(7, [0, 57], np.arange(57), [5], 3, 5)
+    assert [[names[j] for j in row] for row in got] == want
+
+
+def test_select_ctrl_rejects_bad_input(native_lib):
+    with pytest.raises(RuntimeError, match="trait genes"):
+        _native.select_ctrl(0, [0, 3], [0, 1, 2], [5], 2, 5)
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases())
+def test_select_ctrl_geneset_matches_reference_golden(native_lib, path):
+    adata, cov, case = helpers.load_case(path)
+    df_gene = adata.uns["SCDRS_PARAM"]["GENE_STATS"].copy()
+    df_gene["gene"] = df_gene.index
+    genes = sorted(set(case["gene_list"]) & set(df_gene.index))
+    w_of = dict(zip(case["gene_list"], case["gene_weight"]))
+    d_list, d_w = method._select_ctrl_geneset(df_gene, genes, [w_of[g] for g in genes],
+                                              case["ctrl_match_key"], case["n_ctrl"], 200, 0)
+    col = {g: i for i, g in enumerate(adata.var_names)}
+    got = np.array([[col[g] for g in d_list[i]] for i in range(case["n_ctrl"])])
+    assert np.array_equal(got, case["ref_ctrl_idx"])
+    assert np.allclose(np.array([d_w[i] for i in range(case["n_ctrl"])]), case["ref_ctrl_weight"])
+
+
+def test_select_ctrl_geneset_reference_unit_test(native_lib):
+    # restates tests/test_method_score_cell_other.py:10-61 of the reference
+    np.random.seed(0)
+    df_gene = pd.DataFrame(index=["g%d" % i for i in range(1000)],
+                           data={"mean": np.random.rand(1000), "cat": np.random.choice(["a", "b", "c"], 1000)})
+    genes = ["g%d" % i for i in range(0, 100, 2)]
+    weights = list(np.arange(len(genes)) + 1.0)
+    for key, tol in [("mean", 0.1), ("cat", None)]:
+        d_list, d_w = method._select_ctrl_geneset(df_gene, genes, weights, key, 5, 10, 0)
+        o_pos, o_w = orc.select_ctrl_geneset(df_gene.assign(gene=df_gene.index),
+                                             df_gene.index.get_indexer(sorted(genes)),
+                                             [dict(zip(genes, weights))[g] for g in sorted(genes)], key, 5, 10, 0)
+        for i in range(5):
+            assert d_list[i] == list(df_gene.index[o_pos[i]])
+            assert np.allclose(d_w[i], o_w[i])
+            assert len(set(d_list[i])) == len(genes)
+            if tol is not None:
+                # every control gene sits in the same quantile bin as the trait gene it replaces
+                srt = sorted(genes)
+                order = np.argsort(np.searchsorted(np.sort(df_gene["mean"].values), df_gene.loc[srt, "mean"].values) // 100, kind="stable")
+                m_trait = df_gene.loc[[srt[j] for j in order], "mean"].values
+                assert np.all(np.abs(df_gene.loc[d_list[i], "mean"].values - m_trait) < tol + 1e-9)
+
+
+def test_load_gs_formats_and_duplicates(tmp_path):
+    p = tmp_path / "a.gs"
+    p.write_text("TRAIT\tGENESET\nt1\tA,B,C,A\nt2\tA:1.5,B:2,A:3\n")
+    d = util.load_gs(str(p))
+    assert list(d) == ["t1", "t2"]
+    assert d["t1"] == (["A", "B", "C"], [1.0, 1.0, 1.0])
+    assert d["t2"] == (["A", "B"], [3.0, 2.0])           # later duplicate wins
+    d = util.load_gs(str(p), to_intersect=["B", "C"])
+    assert d["t1"][0] == ["B", "C"]
+    p.write_text("TRAIT\tGENESET\nt1\tA:1,B\n")
+    with pytest.raises(ValueError):
+        util.load_gs(str(p))
+    util.save_gs(str(tmp_path / "b.gs"), {"t": (["A", "B"], [1.0, 2.5])})
+    assert util.load_gs(str(tmp_path / "b.gs"))["t"] == (["A", "B"], [1.0, 2.5])
+
+
+def test_load_gs_species_mapping():
+    toy = helpers.TOY
+    mouse = util.load_gs(os.path.join(toy, "toydata_mouse.gs"))
+    human = util.load_gs(os.path.join(toy, "toydata_human.gs"), src_species="hsapiens", dst_species="mmusculus")
+    assert set(human["toydata_gs_human"][0]) <= set(util.load_homolog_mapping("human", "mouse").values())
+    assert len(set(mouse["toydata_gs_mouse"][0]) & set(human["toydata_gs_human"][0])) > 50
+    with pytest.raises(ValueError):
+        util.convert_species_name("zebrafish")
+
+
+def test_read_h5ad_toy_file():
+    adata = helpers.load_toy()[0]
+    assert adata.shape == (30, 2500) and adata.X.nnz == 58179 and adata.X.dtype == np.float32
+    assert list(adata.obs.columns) == ["label", "cell_type", "causal_variable", "non_causal_variable", "covariate"]
+    assert adata.obs["cell_type"].iloc[0] == "causal_cell" and adata.var_names[0] == "Pip4k2a"
+
+
+def test_load_h5ad_checks_and_normalisation(tmp_path):
+    adata = util.load_h5ad(os.path.join(helpers.TOY, "toydata_mouse.h5ad"), flag_filter_data=True,
+                           flag_raw_count=True, min_genes=500, min_cells=5)
+    assert "n_genes" in adata.obs and "n_cells" in adata.var and "n_counts" in adata.obs
+    assert np.allclose(np.expm1(adata.X.toarray()).sum(axis=1), 1e4, rtol=1e-4)
+    assert (adata.obs["n_genes"] >= 500).all()
+
+
+def test_fdr_bh_matches_textbook():
+    p = np.array([0.01, 0.04, 0.03, 0.2, 0.5])
+    want = np.array([0.05, 0.0666666667, 0.0666666667, 0.25, 0.5])
+    assert np.allclose(util.fdr_bh(p), want)
+
+
+def test_score_cell_argument_checks():
+    import scdrs_b200
+    from scdrs_b200.anndata_lite import AnnData
+
+    adata = AnnData(np.zeros((3, 4), dtype=np.float32))
+    with pytest.raises(AssertionError, match="SCDRS_PARAM"):
+        scdrs_b200.score_cell(adata, ["0"])
+    adata.uns["SCDRS_PARAM"] = {}
+    with pytest.raises(AssertionError, match="GENE_STATS"):
+        scdrs_b200.score_cell(adata, ["0"])
+    adata.uns["SCDRS_PARAM"]["GENE_STATS"] = pd.DataFrame({"mean": [0.0] * 4, "var": [0.0] * 4}, index=adata.var_names)
+    with pytest.raises(AssertionError, match="var_tech"):
+        scdrs_b200.score_cell(adata, ["0"])
+    adata.uns["SCDRS_PARAM"]["GENE_STATS"]["var_tech"] = 0.0
+    with pytest.raises(AssertionError, match="ctrl_match_key"):
+        scdrs_b200.score_cell(adata, ["0"])
+    with pytest.raises(AssertionError, match="weight_opt"):
+        scdrs_b200.score_cell(adata, ["0"], ctrl_match_key="mean", weight_opt="bogus")
