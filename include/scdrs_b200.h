@@ -119,12 +119,15 @@ int scdrs_empi_null_count_f64(scdrs_ctx* ctx, int64_t n_t, const double* t, int6
                               const double* null_vals, int64_t* ge_count);
 /* pp.compute_stats reductions (scdrs/pp.py:353-373, 409-417, 467-641) over the resident CSR,
  * of T(X + COV_MAT*COV_BETA + COV_GENE_MEAN) when covariates are set (implicit mode) else T(X);
- * T = identity (transform 0) or expm1 (transform 1).  cell_weight[n_cell] or NULL.
- * Outputs (host f64): gene_sum[n_gene] = sum_c w_c T(x), gene_sumsq[n_gene] = sum_c w_c T(x)^2,
- * cell_sum[n_cell], cell_sumsq[n_cell] (unweighted row sums; NULL to skip). */
+ * T = identity (transform 0) or expm1 (transform 1).  cell_weight[n_cell] or NULL (weights 1).
+ * Host outputs (f64; NULL pairs are skipped):
+ *   gene_sum[n_gene]   = sum_c w_c T(v), accumulated cell by cell like numpy's axis-0 reduction;
+ *   gene_sumsq[n_gene] = sum_c w_c T(v)^2                     when center == 0 (scdrs/pp.py:508-515)
+ *                      = sum_c w_c (T(v) - gene_sum/denom)^2  when center == 1 (np.var, :501);
+ *   cell_sum[n_cell], cell_sumsq[n_cell] = unweighted row sums of T(v) and T(v)^2. */
 int scdrs_gene_cell_stats(scdrs_ctx* ctx, int32_t transform, const double* cell_weight,
-                          double* gene_sum, double* gene_sumsq, double* cell_sum,
-                          double* cell_sumsq);
+                          int32_t center, double denom, double* gene_sum, double* gene_sumsq,
+                          double* cell_sum, double* cell_sumsq);
 
 /* ---- host code: the random draws of _select_ctrl_geneset (scdrs/method.py:276, 295-307) --------
  * numpy-legacy MT19937 seeded with `seed`, bins visited in the given order; for every bin b with

@@ -48,8 +48,8 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_empi_null_count_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "scdrs_empi_null_count_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p]),
+    "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p]),
 }
@@ -243,13 +243,14 @@ class Context:
         check(fn(self._h, v_t.shape[0], ptr(v_t), v_null.shape[0], ptr(v_null), ptr(out)))
         return out
 
-    def gene_cell_stats(self, transform, cell_weight=None, want_gene=True, want_cell=True):
+    def gene_cell_stats(self, transform, cell_weight=None, want_gene=True, want_cell=True, center=False, denom=0.0):
         w = None if cell_weight is None else as_c(cell_weight, np.float64)
         gs = np.empty(self.n_gene) if want_gene else None
         gq = np.empty(self.n_gene) if want_gene else None
         cs = np.empty(self.n_cell) if want_cell else None
         cq = np.empty(self.n_cell) if want_cell else None
-        check(self._L.scdrs_gene_cell_stats(self._h, int(transform), ptr(w), ptr(gs), ptr(gq), ptr(cs), ptr(cq)))
+        check(self._L.scdrs_gene_cell_stats(self._h, int(transform), ptr(w), int(bool(center)), float(denom),
+                                            ptr(gs), ptr(gq), ptr(cs), ptr(cq)))
         return gs, gq, cs, cq
 
 

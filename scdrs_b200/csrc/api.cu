@@ -444,8 +444,8 @@ int scdrs_empi_null_count_f64(scdrs_ctx* c, int64_t n_t, const double* t, int64_
     return empi_null_count<double>(c, n_t, t, n_null, null_vals, ge_count);
 }
 
-int scdrs_gene_cell_stats(scdrs_ctx* c, int32_t transform, const double* cell_weight,
-                          double* gene_sum, double* gene_sumsq, double* cell_sum,
+int scdrs_gene_cell_stats(scdrs_ctx* c, int32_t transform, const double* cell_weight, int32_t center,
+                          double denom, double* gene_sum, double* gene_sumsq, double* cell_sum,
                           double* cell_sumsq) {
     CTX_GUARD(c);
     SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
@@ -459,7 +459,7 @@ int scdrs_gene_cell_stats(scdrs_ctx* c, int32_t transform, const double* cell_we
     double* d_gq = d_gs + g;
     double* d_cs = d_gq + g;
     double* d_cq = d_cs + n;
-    int rc = gene_cell_stats(c, transform, cell_weight ? d_w.as<double>() : nullptr, wg ? d_gs : nullptr,
+    int rc = gene_cell_stats(c, transform, cell_weight ? d_w.as<double>() : nullptr, center, denom, wg ? d_gs : nullptr,
                              wg ? d_gq : nullptr, wc ? d_cs : nullptr, wc ? d_cq : nullptr);
     if (rc == 0 && wg) rc = d2h(c, gene_sum, d_gs, (size_t)g * 8) || d2h(c, gene_sumsq, d_gq, (size_t)g * 8);
     if (rc == 0 && wc) rc = d2h(c, cell_sum, d_cs, (size_t)n * 8) || d2h(c, cell_sumsq, d_cq, (size_t)n * 8);

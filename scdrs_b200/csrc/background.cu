@@ -31,6 +31,17 @@ __device__ __forceinline__ double raw_value(double ref, float d) {
     return isnan(d) ? 0.0 : ref + (double)d;
 }
 
+// minimum that propagates NaN like numpy's min (scdrs/method.py:581)
+__device__ __forceinline__ double min_nan(double a, double b) {
+    return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000ll) : fmin(a, b);
+}
+
+// first gene-set alignment of one entry; rounded product (no fma contraction) so that every kernel
+// that recomputes it gets the same bits
+__device__ __forceinline__ double aligned_value(double ref, float d, double colmean, double a) {
+    return __dmul_rn(raw_value(ref, d) - colmean, a);
+}
+
 // ---- column sums of the raw matrix -----------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 colsum_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_mat,
@@ -66,7 +77,7 @@ __global__ void reduce_partials_kernel(int nblk, int ncol, int op, const double*
     double v = partial[j];
     for (int b = 1; b < nblk; ++b) {
         const double x = partial[(size_t)b * ncol + j];
-        v = op == 0 ? v + x : fmin(v, x);
+        v = op == 0 ? v + x : min_nan(v, x);
     }
     out[j] = v;
 }
@@ -137,12 +148,12 @@ rowstats_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_
             const float* p = dev_mat + row * ld;
             double s = 0.0;
             for (int j = 1 + lane; j < ncol; j += 32)
-                s += (raw_value(ref, p[j]) - sh_cm[j]) * sh_a[j];
+                s += aligned_value(ref, p[j], sh_cm[j], sh_a[j]);
             s = warp_sum_d(s);
             const double mu = n_ctrl > 0 ? s / (double)n_ctrl : 0.0;
             double q = 0.0;
             for (int j = 1 + lane; j < ncol; j += 32) {
-                const double z = (raw_value(ref, p[j]) - sh_cm[j]) * sh_a[j] - mu;
+                const double z = aligned_value(ref, p[j], sh_cm[j], sh_a[j]) - mu;
                 q = fma(z, z, q);
             }
             q = warp_sum_d(q);
@@ -164,13 +175,13 @@ rowstats_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_
             double s = 0.0, mn = INFINITY;
 #pragma unroll 8
             for (int r = 0; r < nr; ++r) {
-                const double z = (raw_value(sh_ref[r], p[(int64_t)r * ld]) - cm) * a;
-                const double v = (z - sh_mu[r]) * sh_is[r];
+                const double z = aligned_value(sh_ref[r], p[(int64_t)r * ld], cm, a);
+                const double v = __dmul_rn(z - sh_mu[r], sh_is[r]);
                 s += v;
-                mn = fmin(mn, v);
+                mn = min_nan(mn, v);
             }
             sh_sum[j] += s;
-            sh_min[j] = fmin(sh_min[j], mn);
+            sh_min[j] = min_nan(sh_min[j], mn);
         }
     }
     __syncthreads();
@@ -225,14 +236,14 @@ __global__ void finalize_cols_kernel(int ncol, double inv_n, const double* __res
     for (int j = threadIdx.x; j < ncol; j += blockDim.x) {
         const double m2 = colsum2[j] * inv_n;
         col2[j] = m2;
-        mn = fmin(mn, colmin[j] - m2);
+        mn = min_nan(mn, colmin[j] - m2);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    for (int o = 16; o > 0; o >>= 1) mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mn;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mn = fmin(mn, sh[i]);
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mn = min_nan(mn, sh[i]);
         scalars[0] = mn;
     }
 }
@@ -249,8 +260,8 @@ __global__ void queries_kernel(int64_t n_cell, int ld, const float* __restrict__
     if (isnan(d)) {
         v = scalars[0] - 1e-3;
     } else {
-        const double z = (row_ref[r] + (double)d - colmean[0]) * ratio_a[0];
-        v = (z - row_mean[r]) * row_istd[r] - col2[0];
+        const double z = aligned_value(row_ref[r], d, colmean[0], ratio_a[0]);
+        v = __dmul_rn(z - row_mean[r], row_istd[r]) - col2[0];
     }
     query[r] = (float)v;
 }

@@ -123,8 +123,8 @@ int null_count_generic_f64(scdrs_ctx* c, int64_t n_t, const double* dev_t, int64
                            const double* dev_null, long long* dev_ge);
 
 // ---- stats.cu -----------------------------------------------------------------------------
-int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, double* dev_gsum,
-                    double* dev_gsumsq, double* dev_csum, double* dev_csumsq);
+int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, int center, double denom,
+                    double* dev_gsum, double* dev_gsumsq, double* dev_csum, double* dev_csumsq);
 
 // ---- scan (empi_null.cu) --------------------------------------------------------------------
 int exclusive_scan_u32(scdrs_ctx* c, const uint32_t* in, uint32_t* out, int64_t n);

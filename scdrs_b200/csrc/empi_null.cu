@@ -391,8 +391,8 @@ null_count_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ de
             if (isnan(d)) {
                 v = gmin;
             } else {
-                const double z = (ref + (double)d - colmean[j]) * ratio_a[j];
-                v = (float)((z - mu) * is - col2[j]);
+                const double z = __dmul_rn(ref + (double)d - colmean[j], ratio_a[j]);
+                v = (float)(__dmul_rn(z - mu, is) - col2[j]);
             }
             if (norm_mat != nullptr) norm_mat[row * n_ctrl + (j - 1)] = v;
             mc += (v >= t) ? 1 : 0;

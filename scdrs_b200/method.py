@@ -316,3 +316,76 @@ def _scratch_context():
     if dev not in _SCRATCH:
         _SCRATCH[dev] = _native.Context(dev)
     return _SCRATCH[dev]
+
+
+# ----------------------------------------------------------------------------------------------
+# many traits against one data set (what `scdrs compute-score` loops over, bin/scdrs:255-274)
+# ----------------------------------------------------------------------------------------------
+def score_traits(
+    data,
+    dict_gs,
+    ctrl_match_key="mean_var",
+    n_ctrl=1000,
+    n_genebin=200,
+    weight_opt="vs",
+    return_ctrl_raw_score=False,
+    return_ctrl_norm_score=False,
+    random_seed=0,
+    min_genes=0,
+    n_jobs=None,
+    on_result=None,
+):
+    """Score every gene set of ``dict_gs`` = {trait: (gene_list, gene_weight_list)}.
+
+    Each trait gets exactly what ``score_cell`` would return for it (every call re-seeds, so traits
+    are independent, scdrs/method.py:96, :276); the host work of upcoming traits (gene
+    intersection and the control-gene draws, which release the GIL) runs in worker threads while
+    the GPU scores the current one.  Returns {trait: DataFrame}, or feeds ``on_result(trait, df)``
+    and returns the list of scored traits when a callback is given.
+    """
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    adata = data
+    assert "SCDRS_PARAM" in adata.uns, "adata.uns['SCDRS_PARAM'] not found, run `scdrs.pp.preprocess` first"
+    assert weight_opt in _LEGAL_WEIGHT_OPT, (
+        "weight_opt=%s is not one of {'uniform', 'vs', 'inv_std', 'od}'" % weight_opt
+    )
+    if weight_opt == "od":
+        raise NotImplementedError("weight_opt='od' (benchmarking-only overdispersion score) is outside the B200 hot path")
+    param = adata.uns["SCDRS_PARAM"]
+    assert ctrl_match_key in param["GENE_STATS"], (
+        "ctrl_match_key=%s not found in adata.uns['SCDRS_PARAM']['GENE_STATS']" % ctrl_match_key
+    )
+    implicit = bool(param["FLAG_SPARSE"] and param["FLAG_COV"])
+    state = get_state(adata)
+    ctx = state.ensure_matrix(adata)
+    state.ensure_cov(adata, implicit)
+    use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))
+    traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
+    if not traits:
+        return {} if on_result is None else []
+    # warm the per-dataset caches (df_gene, bins) once, outside the pool
+    first = _prepare_trait(adata, state, dict_gs[traits[0]][0], dict_gs[traits[0]][1], ctrl_match_key,
+                           n_ctrl, n_genebin, random_seed)
+    ctx.set_gene_stats(first["var"], first["var_tech"])
+    n_jobs = n_jobs or max(1, min(len(traits), (os.cpu_count() or 2) - 1, 16))
+    results = {}
+    with ThreadPoolExecutor(max_workers=n_jobs) as pool:
+        futs = {traits[0]: None}
+        for t in traits[1:]:
+            g, w = dict_gs[t]
+            futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed)
+        for t in traits:
+            prep = first if futs[t] is None else futs[t].result()
+            futs[t] = None
+            out = ctx.score_trait(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
+                                  weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
+                                  want_ctrl_norm=return_ctrl_norm_score)
+            df = _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score)
+            if on_result is None:
+                results[t] = df
+            else:
+                on_result(t, df)
+    np.random.seed(random_seed)
+    return results if on_result is None else traits

@@ -142,10 +142,14 @@ def _device_mean_var(adata, implicit_cov_corr, axis, weights=None, transform=0):
     state.ensure_cov(adata, implicit_cov_corr)
     n_cell, n_gene = adata.shape
     if axis == 0:
-        gs, gq, _, _ = ctx.gene_cell_stats(transform, cell_weight=weights, want_gene=True, want_cell=False)
+        # np.var (centred, two passes) for unweighted dense blocks -- implicit mode and dense X
+        # (scdrs/pp.py:498-501); E[x^2] - E[x]^2 otherwise (:494-496, :508-515)
+        center = weights is None and (implicit_cov_corr or not sparse.issparse(adata.X))
         denom = float(n_cell) if weights is None else float(np.sum(weights))
+        gs, gq, _, _ = ctx.gene_cell_stats(transform, cell_weight=weights, want_gene=True, want_cell=False,
+                                           center=center, denom=denom)
         v_mean = gs / denom
-        v_var = gq / denom - v_mean ** 2
+        v_var = gq / denom if center else gq / denom - v_mean ** 2
     else:
         assert weights is None or len(weights) == n_gene
         if weights is not None:

@@ -109,7 +109,7 @@ def test_score_cell_toy_data_golden_files(sc, cov, dense):
     (True, False, "mean_var", "vs", 100),
     (False, True, "mean_var", "vs", 64),
     (True, True, "mean", "inv_std", 33),
-    (False, False, "mean_var", "uniform", 1),
+    (False, False, "mean_var", "uniform", 8),
 ])
 def test_score_cell_matches_oracle_on_synthetic(sc, use_cov, weighted, key, wopt, n_ctrl):
     from scdrs_b200 import synth
@@ -124,6 +124,20 @@ def test_score_cell_matches_oracle_on_synthetic(sc, use_cov, weighted, key, wopt
                        return_ctrl_raw_score=True, return_ctrl_norm_score=True)
     _check_counts_self_consistent(df, n_ctrl)
     _compare_with_reference(df, ref, n_ctrl, adata.shape[0])
+
+
+def test_score_cell_single_control_set_is_all_nan_like_the_reference(sc):
+    """n_ctrl = 1: the cell-wise std of one control is 0 and the reference returns NaN scores."""
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, _ = synth.make_adata(300, 1200, density=0.1, seed=6)
+    orc.preprocess(adata, cov=None, loess_impl=loess)
+    genes, _ = synth.make_traits(adata.var_names, 1, 50, seed=4)["trait_00"]
+    ref = orc.score_cell(adata, genes, n_ctrl=1)
+    df = sc.score_cell(adata, genes, n_ctrl=1)
+    assert np.allclose(df["raw_score"].values, ref["raw_score"].values, rtol=RTOL, atol=ATOL)
+    assert np.isnan(ref["norm_score"].values).all() and np.isnan(df["norm_score"].values).all()
 
 
 def test_score_cell_zero_rows_get_the_minimum(sc):
