@@ -62,6 +62,7 @@ static void release_all(scdrs_ctx* c) {
     DevBuf* bufs[] = {&c->own_indptr, &c->own_indices, &c->own_data, &c->var, &c->var_tech,
                       &c->cov_mat, &c->cov_beta, &c->gene_mean, &c->set_genes, &c->set_gw, &c->set_w,
                       &c->covM, &c->covm, &c->ratio_a, &c->w_ptr, &c->w_cursor, &c->w_col, &c->w_val,
+                      &c->p_ptr, &c->p_meta, &c->p_col, &c->p_val, &c->colscale, &c->gbase,
                       &c->dev_mat, &c->row_ref, &c->partial, &c->colmean, &c->col2, &c->colmin,
                       &c->row_mean, &c->row_istd, &c->scalars, &c->query, &c->mc_count, &c->norm_mat,
                       &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],

@@ -74,7 +74,9 @@ struct scdrs_ctx {
     int32_t n_ctrl = 0, n_s = 0, n_sc = 0, ncol = 0, ld = 0;  // n_s: trait set size, n_sc: control set size
     bool trait_ready = false;
     scdrs::DevBuf set_genes, set_gw, set_w, covM, covm, ratio_a;  // ratio_a: 1/sqrt(var ratio)
-    scdrs::DevBuf w_ptr, w_cursor, w_col, w_val;
+    scdrs::DevBuf w_ptr, w_cursor, w_col, w_val;        // compact gene-major lists (build scratch)
+    scdrs::DevBuf p_ptr, p_meta, p_col, p_val, colscale, gbase;  // padded / bank-dealt lists the scatter reads
+    bool w_binary = false;
     scdrs::DevBuf dev_mat;   // float [n_cell x ld]: raw score minus the row reference; NaN = exact 0
     scdrs::DevBuf row_ref;   // double [n_cell]
     scdrs::DevBuf partial;   // double scratch for per-CTA column partials

@@ -4,14 +4,22 @@
 // 312-402 of the reference): raw[c, j] = sum_g X[c, g] * W[g, j]  (+ COV_MAT[c,:] . M[:, j] + m[j]
 // in implicit-covariate mode), where column j of W holds the normalised weights of gene set j.
 //
-// Layout: X stays CSR (cells-major, the way cells are sharded across GPUs).  W is stored
-// gene-major ("for gene g: the (set, weight) pairs that contain g"), so that one warp owns one
-// cell, walks that cell's non-zeros once and scatters x * w into 1 + n_ctrl accumulators that
-// live in shared memory.  Lanes split ONE gene's (set, weight) list, so the targets of a warp
-// instruction are distinct columns; no atomics anywhere.  Accumulation is fp64 (the reference
-// accumulates float32 data in float64, scdrs/method.py:392-400); the result is written as an
-// fp64 per-cell reference value plus fp32 deviations from it, with NaN marking exact zeros
-// (the reference's `raw == 0` rule, scdrs/method.py:522-523).
+// Layout.  X stays CSR (cells-major, the way cells are sharded across GPUs).  The weight
+//   w[g, j] = base_g * gw / s_j        (scdrs/method.py:366-375; base = 1, 1/sqrt(var_tech + .01) ...)
+// is factored: base_g is folded into the expression value once per stored entry, 1/s_j is applied
+// once per output column, and only gw (the .gs gene weight; 1 for binary traits, then nothing at
+// all) is kept per (gene, set) pair.  W is stored gene-major: for gene g the list of set ids that
+// contain g.  One warp owns one cell: it walks the cell's non-zeros once and, lanes splitting one
+// gene's list, adds into 1 + n_ctrl fp64 accumulators in shared memory (no atomics: the set ids
+// of one gene are distinct).  The kernel is bound by the shared-memory pipe (one 64-bit load and
+// one 64-bit store per multiply-add), so each gene's list is laid out to make those accesses
+// conflict-free: it is padded to a multiple of 32 slots and its entries are dealt into groups of
+// 16 slots (one shared-memory wavefront each) such that a group holds as few entries of the same
+// bank pair (set id mod 16) as possible.
+//
+// Accumulation is fp64 like the reference's (float32 data times float64 weights,
+// scdrs/method.py:392-400).  The result is written as an fp64 per-cell reference value plus fp32
+// deviations from it, NaN marking exact zeros (the `raw == 0` rule, scdrs/method.py:522-523).
 #include "common.cuh"
 
 namespace scdrs {
@@ -34,52 +42,52 @@ __device__ double block_sum(double v, double* sh) {
     return t;
 }
 
-// One block per gene set: normalised weights (scdrs/method.py:366-375), the covariate
+__device__ __forceinline__ double base_weight(int weight_opt, const double* var, const double* var_tech, int g) {
+    if (weight_opt == SCDRS_WEIGHT_VS) return 1.0 / sqrt(var_tech[g] + 1e-2);
+    if (weight_opt == SCDRS_WEIGHT_INV_STD) return 1.0 / sqrt(var[g] + 1e-2);
+    return 1.0;
+}
+
+__global__ void gene_base_kernel(int n_gene, int weight_opt, const double* __restrict__ var,
+                                 const double* __restrict__ var_tech, double* __restrict__ gbase) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_gene) gbase[g] = base_weight(weight_opt, var, var_tech, g);
+}
+
+// One block per gene set: s_j, the per-entry value the scatter multiplies with, the covariate
 // projections M[:, j] = COV_BETA[S_j]^T w_j and m[j] = COV_GENE_MEAN[S_j] . w_j (:393-394) and the
-// variance-ratio numerator sum_g var_g w_g^2 (:191-195).
-__global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int weight_opt,
+// variance-ratio numerator sum_g var_g w_g^2 (:191-195), w being the normalised weights.
+__global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int binary,
                                  const int32_t* __restrict__ set_genes,
                                  const double* __restrict__ gw,  // [n_s0] trait, then [n_sc] control
                                  const double* __restrict__ explicit_w,
-                                 const double* __restrict__ var, const double* __restrict__ var_tech,
+                                 const double* __restrict__ gbase, const double* __restrict__ var,
                                  const double* __restrict__ beta, const double* __restrict__ gmean,
-                                 float* __restrict__ set_w, double* __restrict__ covM,
-                                 double* __restrict__ covm, double* __restrict__ rnum) {
+                                 float* __restrict__ set_val, double* __restrict__ colscale,
+                                 double* __restrict__ covM, double* __restrict__ covm,
+                                 double* __restrict__ rnum) {
     __shared__ double sh[32];
     const int j = blockIdx.x;
     const int n_s = j == 0 ? n_s0 : n_sc;
     const size_t off = j == 0 ? 0 : (size_t)n_s0 + (size_t)(j - 1) * n_sc;
     const int32_t* genes = set_genes + off;
-    float* wout = set_w + off;
+    float* vout = set_val + off;
+    const double* g = explicit_w != nullptr ? explicit_w + off : gw + (j == 0 ? 0 : n_s0);
     double s = 1.0;
     if (explicit_w == nullptr) {
-        const double* g = gw + (j == 0 ? 0 : n_s0);
         double part = 0.0;
-        for (int p = threadIdx.x; p < n_s; p += blockDim.x) {
-            const int gi = genes[p];
-            double base = 1.0;
-            if (weight_opt == SCDRS_WEIGHT_VS) base = 1.0 / sqrt(var_tech[gi] + 1e-2);
-            if (weight_opt == SCDRS_WEIGHT_INV_STD) base = 1.0 / sqrt(var[gi] + 1e-2);
-            part += base * g[p];
-        }
+        for (int p = threadIdx.x; p < n_s; p += blockDim.x) part += gbase[genes[p]] * g[p];
         s = block_sum(part, sh);
     }
+    // binary sets scatter the constant 1 and fold the common gene weight into the column scale
+    const double cs = binary ? (n_s > 0 ? g[0] : 1.0) / s : 1.0 / s;
     double pm = 0.0, pr = 0.0;
     for (int p = threadIdx.x; p < n_s; p += blockDim.x) {
         const int gi = genes[p];
-        double w;
-        if (explicit_w != nullptr) {
-            w = explicit_w[off + p];
-        } else {
-            const double* g = gw + (j == 0 ? 0 : n_s0);
-            double base = 1.0;
-            if (weight_opt == SCDRS_WEIGHT_VS) base = 1.0 / sqrt(var_tech[gi] + 1e-2);
-            if (weight_opt == SCDRS_WEIGHT_INV_STD) base = 1.0 / sqrt(var[gi] + 1e-2);
-            w = base * g[p] / s;
-        }
-        wout[p] = (float)w;
-        // use the weight the scatter kernel will actually multiply with
-        const double wf = (double)(float)w;
+        const double w = gbase[gi] * g[p] / s;                          // the reference's weight
+        const float val = binary ? 1.0f : (float)g[p];
+        vout[p] = val;
+        const double wf = (double)val * gbase[gi] * cs;                 // the weight actually applied
         if (k > 0) pm += gmean[gi] * wf;
         if (var != nullptr) pr += var[gi] * w * w;
     }
@@ -88,11 +96,12 @@ __global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int weight
     if (threadIdx.x == 0) {
         covm[j] = pm;
         rnum[j] = pr;
+        colscale[j] = cs;
     }
     for (int kk = 0; kk < k; ++kk) {
         double pb = 0.0;
         for (int p = threadIdx.x; p < n_s; p += blockDim.x)
-            pb += beta[(size_t)genes[p] * k + kk] * (double)wout[p];
+            pb += beta[(size_t)genes[p] * k + kk] * ((double)vout[p] * gbase[genes[p]] * cs);
         pb = block_sum(pb, sh);
         if (threadIdx.x == 0) covM[(size_t)kk * ncol + j] = pb;
     }
@@ -116,8 +125,20 @@ __global__ void w_count_kernel(int64_t n_entry, const int32_t* __restrict__ set_
         atomicAdd(&cnt[set_genes[e]], 1u);
 }
 
+__global__ void w_padded_len_kernel(int n_gene, const uint32_t* __restrict__ cnt,
+                                    uint32_t* __restrict__ plen) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_gene) plen[g] = (cnt[g] + 31u) & ~31u;
+    if (g == n_gene) plen[g] = 0;
+}
+
+__global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, uint32_t* __restrict__ meta) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_gene) meta[g] = ((p_ptr[g] >> 5) << 11) | ((p_ptr[g + 1] - p_ptr[g]) >> 5);
+}
+
 __global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t* __restrict__ set_genes,
-                              const float* __restrict__ set_w, const uint32_t* __restrict__ w_ptr,
+                              const float* __restrict__ set_val, const uint32_t* __restrict__ w_ptr,
                               uint32_t* __restrict__ cursor, uint16_t* __restrict__ w_col,
                               float* __restrict__ w_val) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_entry;
@@ -125,28 +146,72 @@ __global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t
         const int g = set_genes[e];
         const uint32_t pos = w_ptr[g] + atomicAdd(&cursor[g], 1u);
         w_col[pos] = (uint16_t)(e < n_s0 ? 0 : 1 + (e - n_s0) / n_sc);
-        w_val[pos] = set_w[e];
+        w_val[pos] = set_val[e];
     }
 }
 
-// Sort each gene's list by column so the layout (and hence the shared-memory access pattern) is
-// reproducible run to run.  Lists are short (about (1+n_ctrl)*n_s/n_gene entries).
-__global__ void w_sort_rows_kernel(int n_gene, const uint32_t* __restrict__ w_ptr,
-                                   uint16_t* __restrict__ w_col, float* __restrict__ w_val) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// padding slots point at 16 scratch accumulators behind the real ones (one per bank pair)
+__global__ void w_pad_init_kernel(int64_t n_slot, int dummy0, uint16_t* __restrict__ col,
+                                  float* __restrict__ val) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_slot;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        col[i] = (uint16_t)(dummy0 + (int)(i & 15));
+        if (val != nullptr) val[i] = 0.f;
+    }
+}
+
+// One warp per gene: deal the gene's entries, ordered by bank pair (set id mod 16), round-robin
+// over its groups of 16 slots.  Entry number i of that order goes to group i % R, slot i / R,
+// R = padded_length / 16, so same-pair entries land in different groups whenever there are at
+// most R of them.
+__global__ void __launch_bounds__(128)
+w_layout_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
+                const uint16_t* __restrict__ w_col, const float* __restrict__ w_val,
+                uint16_t* __restrict__ p_col, float* __restrict__ p_val) {
+    __shared__ uint32_t hist[4][16], run[4][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + warp;
     if (g >= n_gene) return;
     const uint32_t s = w_ptr[g], e = w_ptr[g + 1];
-    for (uint32_t i = s + 1; i < e; ++i) {
-        const uint16_t c = w_col[i];
-        const float v = w_val[i];
-        uint32_t q = i;
-        while (q > s && w_col[q - 1] > c) {
-            w_col[q] = w_col[q - 1];
-            w_val[q] = w_val[q - 1];
-            --q;
+    const uint32_t ps = p_ptr[g], R = (p_ptr[g + 1] - ps) >> 4;
+    if (e == s) return;
+    if (lane < 16) { hist[warp][lane] = 0; run[warp][lane] = 0; }
+    __syncwarp();
+    for (uint32_t t = s + lane; t < e; t += 32) atomicAdd(&hist[warp][w_col[t] & 15], 1u);
+    __syncwarp();
+    // exclusive prefix over the 16 pairs
+    uint32_t h = lane < 16 ? hist[warp][lane] : 0u, inc = h;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncwarp();
+    if (lane < 16) hist[warp][lane] = inc - h;   // now the base of each pair
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t t0 = s; t0 < e; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool ok = t < e;
+        int col = 0, pair = 16 + lane;
+        float v = 0.f;
+        if (ok) {
+            col = w_col[t];
+            v = w_val[t];
+            pair = col & 15;
         }
-        w_col[q] = c;
-        w_val[q] = v;
+        const uint32_t peers = __match_any_sync(0xffffffffu, pair);
+        const uint32_t rank = __popc(peers & lt);
+        uint32_t i = 0;
+        if (ok) i = hist[warp][pair] + run[warp][pair] + rank;
+        __syncwarp();
+        if (ok && rank == 0) run[warp][pair] += __popc(peers);
+        __syncwarp();
+        if (ok) {
+            const uint32_t dst = ps + (i % R) * 16 + (i / R);
+            p_col[dst] = (uint16_t)col;
+            if (p_val != nullptr) p_val[dst] = v;
+        }
     }
 }
 
@@ -179,26 +244,41 @@ static int upload_sets(scdrs_ctx* c, const int32_t* trait_genes, const int32_t* 
     return 0;
 }
 
-static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explicit_w) {
+static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explicit_w, bool binary) {
     const int ncol = c->ncol, n_s = c->n_s, n_sc = c->n_sc, n_gene = c->n_gene;
     const int64_t n_entry = (int64_t)n_s + (int64_t)c->n_ctrl * n_sc;
     SCDRS_TRY(c->covM.reserve((size_t)(c->k > 0 ? c->k : 1) * ncol * sizeof(double)));
     SCDRS_TRY(c->covm.reserve(ncol * sizeof(double)));
+    SCDRS_TRY(c->colscale.reserve(ncol * sizeof(double)));
+    SCDRS_TRY(c->gbase.reserve((size_t)n_gene * sizeof(double)));
     SCDRS_TRY(c->ratio_a.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->colmean.reserve(ncol * sizeof(double)));  // reused as rnum scratch here
     SCDRS_TRY(c->w_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->w_cursor.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+    SCDRS_TRY(c->p_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+    SCDRS_TRY(c->p_meta.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+    SCDRS_CHECK(n_entry + 32 * (int64_t)n_gene < ((int64_t)1 << 26), "gene-set lists too large for the packed index");
+    SCDRS_CHECK(ncol <= 2047 * 32, "too many gene sets");
     SCDRS_TRY(c->w_col.reserve(n_entry * sizeof(uint16_t)));
     SCDRS_TRY(c->w_val.reserve(n_entry * sizeof(float)));
+    // padded size: every non-empty gene rounds up to a multiple of 32 slots
+    const int64_t n_slot_max = n_entry + 31 * (int64_t)(n_gene < n_entry ? n_gene : n_entry);
+    SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
+    if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
+    c->w_binary = binary;
 
+    gene_base_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(
+        n_gene, explicit_w ? SCDRS_WEIGHT_UNIFORM : weight_opt,
+        c->have_stats ? c->var.as<double>() : nullptr,
+        c->have_stats ? c->var_tech.as<double>() : nullptr, c->gbase.as<double>());
+    SCDRS_LAUNCH_CHECK(c);
     double* rnum = c->colmean.as<double>();
     prep_sets_kernel<<<ncol, 256, 0, c->stream>>>(
-        n_s, n_sc, ncol, c->k, weight_opt, c->set_genes.as<int32_t>(), c->set_gw.as<double>(),
-        explicit_w ? c->stage.as<double>() : nullptr,
-        c->have_stats ? c->var.as<double>() : nullptr,
-        c->have_stats ? c->var_tech.as<double>() : nullptr, c->cov_beta.as<double>(),
-        c->gene_mean.as<double>(), c->set_w.as<float>(), c->covM.as<double>(),
-        c->covm.as<double>(), rnum);
+        n_s, n_sc, ncol, c->k, binary ? 1 : 0, c->set_genes.as<int32_t>(), c->set_gw.as<double>(),
+        explicit_w ? c->stage.as<double>() : nullptr, c->gbase.as<double>(),
+        c->have_stats ? c->var.as<double>() : nullptr, c->cov_beta.as<double>(),
+        c->gene_mean.as<double>(), c->set_w.as<float>(), c->colscale.as<double>(),
+        c->covM.as<double>(), c->covm.as<double>(), rnum);
     SCDRS_LAUNCH_CHECK(c);
     ratio_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(ncol, use_var_ratio, rnum,
                                                             c->ratio_a.as<double>());
@@ -210,21 +290,33 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                               c->w_cursor.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     SCDRS_TRY(exclusive_scan_u32(c, c->w_cursor.as<uint32_t>(), c->w_ptr.as<uint32_t>(), n_gene + 1));
+    w_padded_len_kernel<<<(n_gene + 256) / 256, 256, 0, c->stream>>>(n_gene, c->w_cursor.as<uint32_t>(),
+                                                                     c->p_ptr.as<uint32_t>());
+    SCDRS_LAUNCH_CHECK(c);
+    SCDRS_TRY(exclusive_scan_u32(c, c->p_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), n_gene + 1));
+    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(),
+                                                               c->p_meta.as<uint32_t>());
+    SCDRS_LAUNCH_CHECK(c);
     SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
     w_fill_kernel<<<nb, 256, 0, c->stream>>>(n_entry, n_s, n_sc > 0 ? n_sc : 1, c->set_genes.as<int32_t>(),
                                              c->set_w.as<float>(), c->w_ptr.as<uint32_t>(),
                                              c->w_cursor.as<uint32_t>(), c->w_col.as<uint16_t>(),
                                              c->w_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
-    w_sort_rows_kernel<<<(n_gene + 127) / 128, 128, 0, c->stream>>>(
-        n_gene, c->w_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(), c->w_val.as<float>());
+    const int dummy0 = (ncol + 15) & ~15;
+    w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, dummy0, c->p_col.as<uint16_t>(),
+                                                 binary ? nullptr : c->p_val.as<float>());
+    SCDRS_LAUNCH_CHECK(c);
+    w_layout_kernel<<<(n_gene + 3) / 4, 128, 0, c->stream>>>(
+        n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(),
+        c->w_val.as<float>(), c->p_col.as<uint16_t>(), binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
     return 0;
 }
 
 static int set_shape(scdrs_ctx* c, int32_t ncol, int32_t n_s, int32_t n_sc) {
     SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set (call scdrs_set_csr_* first)");
-    SCDRS_CHECK(ncol >= 1 && ncol <= 65535, "1 + n_ctrl = %d outside [1, 65535]", ncol);
+    SCDRS_CHECK(ncol >= 1 && ncol <= 65000, "1 + n_ctrl = %d outside [1, 65000]", ncol);
     SCDRS_CHECK(n_s >= 1, "empty gene set");
     SCDRS_CHECK(n_sc >= 0 && n_sc <= n_s, "control set size %d outside [0, %d]", n_sc, n_s);
     c->n_sc = n_sc;
@@ -245,69 +337,124 @@ int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                 "weight_opt needs gene statistics (call scdrs_set_gene_stats)");
     SCDRS_CHECK(!use_var_ratio || c->have_stats, "variance ratio needs gene statistics");
     SCDRS_TRY(set_shape(c, n_ctrl + 1, n_s, n_s_ctrl));
+    for (int i = 0; i < n_s; ++i) SCDRS_CHECK(trait_genes[i] >= 0 && trait_genes[i] < c->n_gene, "gene index out of range");
+    // binary gene set: every gene weight identical -> the per-entry value is dropped
+    bool binary = true;
+    for (int i = 1; i < n_s && binary; ++i) binary = trait_gw[i] == trait_gw[0];
+    for (int i = 0; i < n_s_ctrl && binary && n_ctrl > 0; ++i) binary = ctrl_gw[i] == trait_gw[0];
     SCDRS_TRY(upload_sets(c, trait_genes, ctrl_genes, trait_gw, ctrl_gw, nullptr));
-    return build_w(c, weight_opt, use_var_ratio, false);
+    return build_w(c, weight_opt, use_var_ratio, false, binary);
 }
 
 int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
                      const double* w) {
     SCDRS_TRY(set_shape(c, n_set, n_s, n_s));
     SCDRS_TRY(upload_sets(c, nullptr, genes, nullptr, nullptr, w));
-    return build_w(c, SCDRS_WEIGHT_UNIFORM, 0, true);
+    return build_w(c, SCDRS_WEIGHT_UNIFORM, 0, true, false);
 }
 
 // ---- the scatter kernel ----------------------------------------------------------------------
-// One warp per cell.  acc[] (1 + n_ctrl doubles) lives in shared memory.
+// One warp per cell.  acc[] (1 + n_ctrl fp64 accumulators + 16 scratch ones) lives in shared memory.
+// p_meta[g] = (first 32-slot block of gene g's list << 11) | number of 32-slot blocks.
+__device__ __forceinline__ void acc_add(uint32_t acc_s, uint32_t col, double x) {
+    const uint32_t a = acc_s + col * 8u;
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    v += x;
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void acc_fma(uint32_t acc_s, uint32_t col, double x, float w) {
+    const uint32_t a = acc_s + col * 8u;
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    v = fma(x, (double)w, v);
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                  const float* __restrict__ data, const uint32_t* __restrict__ w_ptr,
-                  const uint16_t* __restrict__ w_col, const float* __restrict__ w_val, int k,
+                  const float* __restrict__ data, const double* __restrict__ gbase,
+                  const uint32_t* __restrict__ p_meta, const uint16_t* __restrict__ p_col,
+                  const float* __restrict__ p_val, const double* __restrict__ colscale, int k,
                   const double* __restrict__ cov_mat, const double* __restrict__ covM,
                   const double* __restrict__ covm, float* __restrict__ dev_mat,
                   double* __restrict__ row_ref) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = reinterpret_cast<double*>(smem_raw) + (size_t)warp * acc_stride;
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    const uint32_t dummy = (uint32_t)(acc_stride - 16 + (lane & 15));
 
     for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell;
          row += (int64_t)gridDim.x * wpb) {
-        for (int j = lane; j < ncol; j += 32) acc[j] = 0.0;
+        for (int j = lane; j < acc_stride; j += 32) acc[j] = 0.0;
         __syncwarp();
         const int64_t p0 = indptr[row], p1 = indptr[row + 1];
         for (int64_t base = p0; base < p1; base += 32) {
             const int64_t q = base + lane;
-            uint32_t ws = 0, we = 0;
-            float x = 0.f;
+            uint32_t meta = 0;
+            double xd = 0.0;
             if (q < p1) {
                 const int g = indices[q];
-                x = data[q];
-                ws = w_ptr[g];
-                we = w_ptr[g + 1];
+                xd = (double)data[q] * gbase[g];
+                meta = p_meta[g];
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
+            // software pipeline: the set ids of entry i + 1 are fetched while entry i is applied
+            uint32_t m = __shfl_sync(0xffffffffu, meta, 0);
+            uint32_t t = ((m >> 11) << 5) + lane, nb = m & 2047u;
+            uint32_t c0 = nb > 0 ? p_col[t] : dummy, c1 = nb > 1 ? p_col[t + 32] : dummy;
+            float w0 = 0.f, w1 = 0.f;
+            if (WEIGHTED) {
+                w0 = nb > 0 ? p_val[t] : 0.f;
+                w1 = nb > 1 ? p_val[t + 32] : 0.f;
+            }
             for (int i = 0; i < n; ++i) {
-                const uint32_t s = __shfl_sync(0xffffffffu, ws, i);
-                const uint32_t e = __shfl_sync(0xffffffffu, we, i);
-                const double xi = (double)__shfl_sync(0xffffffffu, x, i);
-                for (uint32_t t = s + lane; t < e; t += 32) {
-                    const int col = w_col[t];
-                    acc[col] = fma(xi, (double)w_val[t], acc[col]);
+                const double xi = __shfl_sync(0xffffffffu, xd, i);
+                const uint32_t tc = t, nbc = nb, a0 = c0, a1 = c1;
+                const float v0 = w0, v1 = w1;
+                if (i + 1 < n) {
+                    m = __shfl_sync(0xffffffffu, meta, i + 1);
+                    t = ((m >> 11) << 5) + lane;
+                    nb = m & 2047u;
+                    c0 = nb > 0 ? p_col[t] : dummy;
+                    c1 = nb > 1 ? p_col[t + 32] : dummy;
+                    if (WEIGHTED) {
+                        w0 = nb > 0 ? p_val[t] : 0.f;
+                        w1 = nb > 1 ? p_val[t + 32] : 0.f;
+                    }
+                }
+                if (WEIGHTED) {
+                    acc_fma(acc_s, a0, xi, v0);
+                    acc_fma(acc_s, a1, xi, v1);
+                } else {
+                    acc_add(acc_s, a0, xi);
+                    acc_add(acc_s, a1, xi);
+                }
+#pragma unroll 1
+                for (uint32_t b = 2; b < nbc; ++b) {      // long lists (rare)
+                    const uint32_t col = p_col[tc + b * 32];
+                    if (WEIGHTED)
+                        acc_fma(acc_s, col, xi, p_val[tc + b * 32]);
+                    else
+                        acc_add(acc_s, col, xi);
                 }
                 __syncwarp();
             }
         }
-        // epilogue: covariate terms, row reference, deviations
+        // epilogue: column scale, covariate terms, row reference, deviations
         double rs = 0.0;
         for (int j = lane; j < ncol; j += 32) {
-            double v = acc[j];
+            double v = acc[j] * colscale[j];
             if (k > 0) {
                 double cterm = covm[j];
                 for (int kk = 0; kk < k; ++kk)
                     cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
                 v += cterm;
-                acc[j] = v;
             }
+            acc[j] = v;
             rs += v;
         }
         rs = warp_sum(rs);
@@ -326,32 +473,39 @@ int spmm_score(scdrs_ctx* c) {
     const int ncol = c->ncol;
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
-    const int acc_stride = (ncol + 1) & ~1;
+    const int acc_stride = ((ncol + 15) & ~15) + 16;   // + 16 scratch slots for padding entries
     const size_t per_warp = (size_t)acc_stride * sizeof(double);
     SCDRS_CHECK(per_warp <= 200 * 1024, "1 + n_ctrl = %d needs more shared memory than one SM has", ncol);
-    int wpb = (int)((64 * 1024) / per_warp);
+    int wpb = (int)((72 * 1024) / per_warp);
     if (wpb > 8) wpb = 8;
     if (wpb < 1) wpb = 1;
     const size_t smem = per_warp * wpb;
     static bool attr_set = false;
     if (!attr_set) {
-        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
+        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    int per_sm = (int)((226 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm * wpb > 48) per_sm = 48 / wpb;
+    if (per_sm * wpb > 64) per_sm = 64 / wpb;
     int64_t grid = (int64_t)kNumSM * per_sm;
     const int64_t need = (c->n_cell + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    spmm_score_kernel<<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-        c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data,
-        c->w_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(), c->w_val.as<float>(), c->k,
-        c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(),
-        c->dev_mat.as<float>(), c->row_ref.as<double>());
+    if (c->w_binary)
+        spmm_score_kernel<false><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->gbase.as<double>(),
+            c->p_meta.as<uint32_t>(), c->p_col.as<uint16_t>(), nullptr, c->colscale.as<double>(), c->k,
+            c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->dev_mat.as<float>(),
+            c->row_ref.as<double>());
+    else
+        spmm_score_kernel<true><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->gbase.as<double>(),
+            c->p_meta.as<uint32_t>(), c->p_col.as<uint16_t>(), c->p_val.as<float>(), c->colscale.as<double>(),
+            c->k, c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(),
+            c->dev_mat.as<float>(), c->row_ref.as<double>());
     SCDRS_LAUNCH_CHECK(c);
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->trait_ready = true;
