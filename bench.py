@@ -334,9 +334,9 @@ def main():
     ctx.set_gene_stats(preps[0]["var"], preps[0]["var_tech"])
 
     if world > 1:
-        from scdrs_b200.distributed import ShardedScorer
+        from scdrs_b200.distributed import CudaPhases, ShardedScorer
 
-        scorer = ShardedScorer(ctx, n_cell, device)
+        scorer = ShardedScorer(CudaPhases(ctx, device), device)
         def run_trait(p):
             return scorer.score(p["trait_cols"], p["trait_gw"], p["ctrl_cols"], p["ctrl_gw"], "vs", True)
     else:

@@ -246,7 +246,7 @@ def score_cell(
         return df, dict(
             ctrl_cols=col_of[ctrl_pos], trait_cols=col_of[trait_pos], mc_count=mc_count,
             ge_count=ge, ratio=ratio, mat_raw=mat_raw, mat_norm=mat_norm, v_raw=v_raw,
-            v_norm=v_norm, trait_w=v_w, ctrl_w=mat_w,
+            v_norm=v_norm, trait_w=v_w, ctrl_w=mat_w, ctrl_gw_raw=ctrl_gw[0] if n_ctrl > 0 else np.zeros(0),
         )
     return df
 

@@ -150,12 +150,11 @@ __global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t
     }
 }
 
-// padding slots point at 16 scratch accumulators behind the real ones (one per bank pair)
-__global__ void w_pad_init_kernel(int64_t n_slot, int dummy0, uint16_t* __restrict__ col,
-                                  float* __restrict__ val) {
+// padding slots carry the set id 0xffff, which the scatter kernel predicates off
+__global__ void w_pad_init_kernel(int64_t n_slot, uint16_t* __restrict__ col, float* __restrict__ val) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_slot;
          i += (int64_t)gridDim.x * blockDim.x) {
-        col[i] = (uint16_t)(dummy0 + (int)(i & 15));
+        col[i] = (uint16_t)0xffff;
         if (val != nullptr) val[i] = 0.f;
     }
 }
@@ -303,8 +302,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                              c->w_cursor.as<uint32_t>(), c->w_col.as<uint16_t>(),
                                              c->w_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
-    const int dummy0 = (ncol + 15) & ~15;
-    w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, dummy0, c->p_col.as<uint16_t>(),
+    w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, c->p_col.as<uint16_t>(),
                                                  binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
     w_layout_kernel<<<(n_gene + 3) / 4, 128, 0, c->stream>>>(
@@ -354,21 +352,33 @@ int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* ge
 }
 
 // ---- the scatter kernel ----------------------------------------------------------------------
-// One warp per cell.  acc[] (1 + n_ctrl fp64 accumulators + 16 scratch ones) lives in shared memory.
+// One warp per cell.  acc[] (1 + n_ctrl fp64 accumulators) lives in shared memory.
 // p_meta[g] = (first 32-slot block of gene g's list << 11) | number of 32-slot blocks.
+// Padding slots carry the set id 0xffff and are predicated off, so they touch no bank.
 __device__ __forceinline__ void acc_add(uint32_t acc_s, uint32_t col, double x) {
-    const uint32_t a = acc_s + col * 8u;
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
-    v += x;
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 v;\n\t.reg .u32 a;\n\t"
+        "setp.ne.u32 p, %1, 0xffff;\n\t"
+        "mad.lo.u32 a, %1, 8, %0;\n\t"
+        "mov.f64 v, 0d0000000000000000;\n\t"
+        "@p ld.shared.f64 v, [a];\n\t"
+        "add.f64 v, v, %2;\n\t"
+        "@p st.shared.f64 [a], v;\n\t}"
+        ::"r"(acc_s), "r"(col), "d"(x)
+        : "memory");
 }
 __device__ __forceinline__ void acc_fma(uint32_t acc_s, uint32_t col, double x, float w) {
-    const uint32_t a = acc_s + col * 8u;
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
-    v = fma(x, (double)w, v);
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 v, wd;\n\t.reg .u32 a;\n\t"
+        "setp.ne.u32 p, %1, 0xffff;\n\t"
+        "mad.lo.u32 a, %1, 8, %0;\n\t"
+        "cvt.f64.f32 wd, %3;\n\t"
+        "mov.f64 v, 0d0000000000000000;\n\t"
+        "@p ld.shared.f64 v, [a];\n\t"
+        "fma.rn.f64 v, %2, wd, v;\n\t"
+        "@p st.shared.f64 [a], v;\n\t}"
+        ::"r"(acc_s), "r"(col), "d"(x), "f"(w)
+        : "memory");
 }
 
 template <bool WEIGHTED>
@@ -385,7 +395,7 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = reinterpret_cast<double*>(smem_raw) + (size_t)warp * acc_stride;
     const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
-    const uint32_t dummy = (uint32_t)(acc_stride - 16 + (lane & 15));
+    const uint32_t dummy = 0xffffu;
 
     for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell;
          row += (int64_t)gridDim.x * wpb) {
@@ -473,7 +483,7 @@ int spmm_score(scdrs_ctx* c) {
     const int ncol = c->ncol;
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
-    const int acc_stride = ((ncol + 15) & ~15) + 16;   // + 16 scratch slots for padding entries
+    const int acc_stride = (ncol + 15) & ~15;
     const size_t per_warp = (size_t)acc_stride * sizeof(double);
     SCDRS_CHECK(per_warp <= 200 * 1024, "1 + n_ctrl = %d needs more shared memory than one SM has", ncol);
     int wpb = (int)((72 * 1024) / per_warp);

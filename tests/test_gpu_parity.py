@@ -287,3 +287,94 @@ def test_compute_stats_modes_agree(sc):
     c1, c2 = a_sp.uns["SCDRS_PARAM"]["CELL_STATS"], a_dn.uns["SCDRS_PARAM"]["CELL_STATS"]
     assert np.allclose(c1["mean"].values.astype(float), c2["mean"].values.astype(float), rtol=1e-4, atol=1e-6)
     assert np.allclose(c1["var"].values.astype(float), c2["var"].values.astype(float), rtol=1e-3, atol=1e-6)
+
+
+def test_cli_compute_score_on_toy_data(sc, tmp_path):
+    """tests/test_CLI.py:10-71 of the reference: mouse and human gene sets give identical p-values and
+    the cov run reproduces the golden score file."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for species, gs in [("mouse", "toydata_mouse.gs"), ("human", "toydata_human.gs")]:
+        cmd = [sys.executable, os.path.join(root, "bin", "scdrs"), "compute-score",
+               "--h5ad-file", os.path.join(helpers.TOY, "toydata_mouse.h5ad"), "--h5ad-species", "mouse",
+               "--gs-file", os.path.join(helpers.TOY, gs), "--gs-species", species,
+               "--cov-file", os.path.join(helpers.TOY, "toydata_mouse.cov"), "--ctrl-match-opt", "mean_var",
+               "--n-ctrl", "20", "--flag-filter-data", "False", "--weight-opt", "vs", "--flag-raw-count", "False",
+               "--flag-return-ctrl-raw-score", "False", "--flag-return-ctrl-norm-score", "True",
+               "--out-folder", str(tmp_path)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "FDR<0.1 cells" in r.stdout
+    mouse = pd.read_csv(tmp_path / "toydata_gs_mouse.score.gz", sep="\t", index_col=0)
+    human = pd.read_csv(tmp_path / "toydata_gs_human.score.gz", sep="\t", index_col=0)
+    assert np.allclose(mouse["pval"].values, human["pval"].values)
+    gold = helpers.load_toy()[3]["REF_COV"]
+    assert list(mouse.columns) == list(gold.columns) and list(mouse.index) == list(gold.index)
+    # the reference's own CLI test skips norm_score / pval: live mean_var bins may differ (tests/test_CLI.py:58-69)
+    assert np.allclose(mouse["raw_score"].values, gold["raw_score"].values, rtol=1e-2)
+    full = pd.read_csv(tmp_path / "toydata_gs_mouse.full_score.gz", sep="\t", index_col=0)
+    assert full.shape == (30, 26)
+
+
+def test_phases_on_two_shards_equal_single_context(native_lib):
+    """The multi-GPU phase API with the collectives done by hand: two contexts on one GPU, each
+    holding half of the cells, must reproduce the single-context result (counts exactly)."""
+    import torch
+
+    from scdrs_b200 import _native, synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(1001, 2000, density=0.1, seed=12)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    param = adata.uns["SCDRS_PARAM"]
+    genes, w = synth.make_traits(adata.var_names, 1, 150, weighted=True, seed=5)["trait_00"]
+    _, info = orc.score_cell(adata, genes, gene_weight=w, n_ctrl=50, return_internals=True)
+    idx = adata.var_names.get_indexer(sorted(set(genes)))
+    w_of = dict(zip(genes, w))
+    tgw = np.array([w_of[g] for g in sorted(set(genes))])
+    gs = param["GENE_STATS"]
+
+    def make_ctx(lo, hi):
+        X = adata.X[lo:hi].tocsr()
+        c = _native.Context(0)
+        c.set_csr_host(X.indptr, X.indices, X.data, X.shape[1])
+        c.set_gene_stats(gs["var"].values.astype(float), gs["var_tech"].values.astype(float))
+        c.set_cov(param["COV_MAT"].values[lo:hi], param["COV_BETA"].values, param["COV_GENE_MEAN"].values)
+        return c
+
+    n = adata.shape[0]
+    full = make_ctx(0, n).score_trait(idx, tgw, info["ctrl_cols"], info["ctrl_gw_raw"], "vs", True, want_ctrl_norm=True)
+    shards = [(0, 400), (400, n)]
+    ctxs = [make_ctx(lo, hi) for lo, hi in shards]
+    ncol = 51
+    dev = torch.device("cuda", 0)
+    t = lambda m, dt=torch.float64: torch.zeros(m, dtype=dt, device=dev)
+    colsum = [t(ncol) for _ in ctxs]
+    torch.cuda.synchronize()      # the contexts run on their own streams
+    for c, cs in zip(ctxs, colsum):
+        c.trait_raw(idx, tgw, info["ctrl_cols"], info["ctrl_gw_raw"], "vs", True, cs.data_ptr()); c.sync()
+    tot = colsum[0] + colsum[1]
+    col2, cmin = [t(ncol) for _ in ctxs], [t(ncol) for _ in ctxs]
+    torch.cuda.synchronize()
+    for c, a, b in zip(ctxs, col2, cmin):
+        c.trait_rowstats(tot.data_ptr(), n, a.data_ptr(), b.data_ptr()); c.sync()
+    col2t, cmint = col2[0] + col2[1], torch.minimum(cmin[0], cmin[1])
+    q = [t(hi - lo, torch.float32) for lo, hi in shards]
+    torch.cuda.synchronize()
+    for c, qq in zip(ctxs, q):
+        c.trait_queries(col2t.data_ptr(), cmint.data_ptr(), qq.data_ptr()); c.sync()
+    q_all = torch.cat(q)
+    hist = [t(n + 1, torch.int64) for _ in ctxs]
+    torch.cuda.synchronize()
+    for c, h in zip(ctxs, hist):
+        c.trait_count(q_all.data_ptr(), n, h.data_ptr()); c.sync()
+    hist_t = hist[0] + hist[1]
+    torch.cuda.synchronize()
+    outs = [c.trait_finish(hist_t.data_ptr(), n, lo, n * 50, 50, want_ctrl_norm=True) for c, (lo, hi) in zip(ctxs, shards)]
+    for key in ["ge_count", "mc_count"]:
+        assert np.array_equal(np.concatenate([o[key] for o in outs]), full[key]), key
+    for key in ["raw_score", "norm_score", "ctrl_norm"]:
+        assert np.allclose(np.concatenate([o[key] for o in outs]), full[key], rtol=1e-6, atol=1e-6), key

@@ -170,3 +170,20 @@ def test_score_cell_argument_checks():
         scdrs_b200.score_cell(adata, ["0"])
     with pytest.raises(AssertionError, match="weight_opt"):
         scdrs_b200.score_cell(adata, ["0"], ctrl_match_key="mean", weight_opt="bogus")
+
+
+def test_cli_flag_parsing():
+    from scdrs_b200 import cli
+
+    cmd, kw = cli.parse_cli(["compute-score", "--h5ad-file", "a.h5ad", "--h5ad_species=mouse", "--gs-file", "g.gs",
+                             "--gs-species", "mouse", "--out-folder", "o", "--n-ctrl", "20",
+                             "--flag-filter-data", "False", "--flag_raw_count=False", "--cov-file", "None"])
+    assert cmd == "compute_score" and kw["n_ctrl"] == 20 and kw["flag_filter_data"] is False
+    assert kw["flag_raw_count"] is False and kw["cov_file"] is None and kw["flag_return_ctrl_norm_score"] is True
+    assert kw["ctrl_match_opt"] == "mean_var" and kw["weight_opt"] == "vs" and kw["min_genes"] == 250
+    with pytest.raises(SystemExit):
+        cli.parse_cli(["compute-score", "--bogus", "1"])
+    with pytest.raises(SystemExit):
+        cli.main(["munge-gs", "--out-file", "x"])
+    with pytest.raises(ValueError):
+        cli.compute_score("a", "mouse", "g", "mouse", "o", ctrl_match_opt="bad")
