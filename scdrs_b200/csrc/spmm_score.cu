@@ -13,7 +13,7 @@
 // gene's list, adds into 1 + n_ctrl fp64 accumulators in shared memory (no atomics: the set ids
 // of one gene are distinct).  The kernel is bound by the shared-memory pipe (one 64-bit load and
 // one 64-bit store per multiply-add), so each gene's list is laid out to make those accesses
-// conflict-free: it is padded to a multiple of 32 slots and its entries are dealt into groups of
+// conflict-free: it is padded to a multiple of 16 slots and its entries are dealt into groups of
 // 16 slots (one shared-memory wavefront each) such that a group holds as few entries of the same
 // bank pair (set id mod 16) as possible.
 //
@@ -128,13 +128,13 @@ __global__ void w_count_kernel(int64_t n_entry, const int32_t* __restrict__ set_
 __global__ void w_padded_len_kernel(int n_gene, const uint32_t* __restrict__ cnt,
                                     uint32_t* __restrict__ plen) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_gene) plen[g] = (cnt[g] + 31u) & ~31u;
+    if (g < n_gene) plen[g] = (cnt[g] + 15u) & ~15u;
     if (g == n_gene) plen[g] = 0;
 }
 
 __global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, uint32_t* __restrict__ meta) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_gene) meta[g] = ((p_ptr[g] >> 5) << 11) | ((p_ptr[g + 1] - p_ptr[g]) >> 5);
+    if (g < n_gene) meta[g] = ((p_ptr[g] >> 4) << 12) | ((p_ptr[g + 1] - p_ptr[g]) >> 4);
 }
 
 __global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t* __restrict__ set_genes,
@@ -256,12 +256,12 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_TRY(c->w_cursor.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_meta.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
-    SCDRS_CHECK(n_entry + 32 * (int64_t)n_gene < ((int64_t)1 << 26), "gene-set lists too large for the packed index");
-    SCDRS_CHECK(ncol <= 2047 * 32, "too many gene sets");
+    SCDRS_CHECK(n_entry + 16 * (int64_t)n_gene < ((int64_t)1 << 24), "gene-set lists too large for the packed index");
+    SCDRS_CHECK(ncol <= 4095 * 16, "too many gene sets");
     SCDRS_TRY(c->w_col.reserve(n_entry * sizeof(uint16_t)));
     SCDRS_TRY(c->w_val.reserve(n_entry * sizeof(float)));
     // padded size: every non-empty gene rounds up to a multiple of 32 slots
-    const int64_t n_slot_max = n_entry + 31 * (int64_t)(n_gene < n_entry ? n_gene : n_entry);
+    const int64_t n_slot_max = n_entry + 15 * (int64_t)(n_gene < n_entry ? n_gene : n_entry);
     SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
     if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
     c->w_binary = binary;
@@ -352,8 +352,6 @@ int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* ge
 }
 
 // ---- the scatter kernel ----------------------------------------------------------------------
-// One warp per cell.  acc[] (1 + n_ctrl fp64 accumulators) lives in shared memory.
-// p_meta[g] = (first 32-slot block of gene g's list << 11) | number of 32-slot blocks.
 // Padding slots carry the set id 0xffff and are predicated off, so they touch no bank.
 __device__ __forceinline__ void acc_add(uint32_t acc_s, uint32_t col, double x) {
     asm volatile(
@@ -381,6 +379,57 @@ __device__ __forceinline__ void acc_fma(uint32_t acc_s, uint32_t col, double x, 
         : "memory");
 }
 
+// Two independent read-modify-writes (the set ids of one gene are distinct, so the addresses
+// differ): loads first, then adds, then stores, to overlap the shared-memory latencies.
+__device__ __forceinline__ void acc_add2(uint32_t acc_s, uint32_t q0, uint32_t q1, double x) {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1;\n\t.reg .f64 v0, v1;\n\t.reg .u32 a0, a1;\n\t"
+        "setp.ne.u32 p0, %1, 0xffff;\n\tsetp.ne.u32 p1, %2, 0xffff;\n\t"
+        "mad.lo.u32 a0, %1, 8, %0;\n\tmad.lo.u32 a1, %2, 8, %0;\n\t"
+        "mov.f64 v0, 0d0000000000000000;\n\tmov.f64 v1, v0;\n\t"
+        "@p0 ld.shared.f64 v0, [a0];\n\t@p1 ld.shared.f64 v1, [a1];\n\t"
+        "add.f64 v0, v0, %3;\n\tadd.f64 v1, v1, %3;\n\t"
+        "@p0 st.shared.f64 [a0], v0;\n\t@p1 st.shared.f64 [a1], v1;\n\t}"
+        ::"r"(acc_s), "r"(q0), "r"(q1), "d"(x)
+        : "memory");
+}
+__device__ __forceinline__ void acc_fma2(uint32_t acc_s, uint32_t q0, uint32_t q1, double x, float w0, float w1) {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1;\n\t.reg .f64 v0, v1, d0, d1;\n\t.reg .u32 a0, a1;\n\t"
+        "setp.ne.u32 p0, %1, 0xffff;\n\tsetp.ne.u32 p1, %2, 0xffff;\n\t"
+        "mad.lo.u32 a0, %1, 8, %0;\n\tmad.lo.u32 a1, %2, 8, %0;\n\t"
+        "cvt.f64.f32 d0, %4;\n\tcvt.f64.f32 d1, %5;\n\t"
+        "mov.f64 v0, 0d0000000000000000;\n\tmov.f64 v1, v0;\n\t"
+        "@p0 ld.shared.f64 v0, [a0];\n\t@p1 ld.shared.f64 v1, [a1];\n\t"
+        "fma.rn.f64 v0, %3, d0, v0;\n\tfma.rn.f64 v1, %3, d1, v1;\n\t"
+        "@p0 st.shared.f64 [a0], v0;\n\t@p1 st.shared.f64 [a1], v1;\n\t}"
+        ::"r"(acc_s), "r"(q0), "r"(q1), "d"(x), "f"(w0), "f"(w1)
+        : "memory");
+}
+
+// the first 64 slots (four 16-slot groups) of one gene's list, as seen by one lane of the warp:
+// lanes 0-15 read groups 0 and 2, lanes 16-31 groups 1 and 3
+struct GeneSlots {
+    uint32_t c0, c1, t, ng;
+    float w0, w1;
+};
+
+template <bool WEIGHTED>
+__device__ __forceinline__ void fetch_slots(GeneSlots& s, uint32_t m, uint32_t lane,
+                                            const uint16_t* __restrict__ p_col,
+                                            const float* __restrict__ p_val) {
+    const uint32_t grp = lane >> 4;
+    s.t = ((m >> 12) << 4) + lane;
+    s.ng = m & 4095u;
+    s.c0 = grp < s.ng ? p_col[s.t] : 0xffffu;
+    s.c1 = grp + 2 < s.ng ? p_col[s.t + 32] : 0xffffu;
+    if (WEIGHTED) {
+        s.w0 = grp < s.ng ? p_val[s.t] : 0.f;
+        s.w1 = grp + 2 < s.ng ? p_val[s.t + 32] : 0.f;
+    }
+}
+
+// One warp per cell.  p_meta[g] = (first 16-slot group of gene g's list << 12) | number of groups.
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
@@ -395,7 +444,6 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = reinterpret_cast<double*>(smem_raw) + (size_t)warp * acc_stride;
     const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
-    const uint32_t dummy = 0xffffu;
 
     for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell;
          row += (int64_t)gridDim.x * wpb) {
@@ -412,46 +460,38 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
                 meta = p_meta[g];
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
-            // software pipeline: the set ids of entry i + 1 are fetched while entry i is applied
-            uint32_t m = __shfl_sync(0xffffffffu, meta, 0);
-            uint32_t t = ((m >> 11) << 5) + lane, nb = m & 2047u;
-            uint32_t c0 = nb > 0 ? p_col[t] : dummy, c1 = nb > 1 ? p_col[t + 32] : dummy;
-            float w0 = 0.f, w1 = 0.f;
-            if (WEIGHTED) {
-                w0 = nb > 0 ? p_val[t] : 0.f;
-                w1 = nb > 1 ? p_val[t + 32] : 0.f;
-            }
-            for (int i = 0; i < n; ++i) {
+            // software pipeline, two entries deep: while entry i is applied, the set ids of entries
+            // i + 1 and i + 2 are in flight
+            GeneSlots sa, sb;
+            fetch_slots<WEIGHTED>(sa, __shfl_sync(0xffffffffu, meta, 0), lane, p_col, p_val);
+            fetch_slots<WEIGHTED>(sb, n > 1 ? __shfl_sync(0xffffffffu, meta, 1) : 0u, lane, p_col, p_val);
+            auto step = [&](GeneSlots& cur, int i) {
+                const uint32_t q0 = cur.c0, q1 = cur.c1, tc = cur.t, ngc = cur.ng;
+                const float v0 = cur.w0, v1 = cur.w1;
                 const double xi = __shfl_sync(0xffffffffu, xd, i);
-                const uint32_t tc = t, nbc = nb, a0 = c0, a1 = c1;
-                const float v0 = w0, v1 = w1;
-                if (i + 1 < n) {
-                    m = __shfl_sync(0xffffffffu, meta, i + 1);
-                    t = ((m >> 11) << 5) + lane;
-                    nb = m & 2047u;
-                    c0 = nb > 0 ? p_col[t] : dummy;
-                    c1 = nb > 1 ? p_col[t + 32] : dummy;
-                    if (WEIGHTED) {
-                        w0 = nb > 0 ? p_val[t] : 0.f;
-                        w1 = nb > 1 ? p_val[t + 32] : 0.f;
+                uint32_t m = __shfl_sync(0xffffffffu, meta, (i + 2) & 31);
+                if (i + 2 >= n) m = 0;
+                fetch_slots<WEIGHTED>(cur, m, lane, p_col, p_val);
+                if (WEIGHTED)
+                    acc_fma2(acc_s, q0, q1, xi, v0, v1);
+                else
+                    acc_add2(acc_s, q0, q1, xi);
+                if (ngc > 4) {                                   // long lists (rare); warp-uniform
+#pragma unroll 1
+                    for (uint32_t gi = 4 + (lane >> 4); gi < ngc; gi += 2) {
+                        const uint32_t col = p_col[tc + (gi - (lane >> 4)) * 16];
+                        if (WEIGHTED)
+                            acc_fma(acc_s, col, xi, p_val[tc + (gi - (lane >> 4)) * 16]);
+                        else
+                            acc_add(acc_s, col, xi);
                     }
                 }
-                if (WEIGHTED) {
-                    acc_fma(acc_s, a0, xi, v0);
-                    acc_fma(acc_s, a1, xi, v1);
-                } else {
-                    acc_add(acc_s, a0, xi);
-                    acc_add(acc_s, a1, xi);
-                }
-#pragma unroll 1
-                for (uint32_t b = 2; b < nbc; ++b) {      // long lists (rare)
-                    const uint32_t col = p_col[tc + b * 32];
-                    if (WEIGHTED)
-                        acc_fma(acc_s, col, xi, p_val[tc + b * 32]);
-                    else
-                        acc_add(acc_s, col, xi);
-                }
                 __syncwarp();
+            };
+#pragma unroll 1
+            for (int i = 0; i < n; i += 2) {
+                step(sa, i);
+                if (i + 1 < n) step(sb, i + 1);
             }
         }
         // epilogue: column scale, covariate terms, row reference, deviations
@@ -484,7 +524,7 @@ int spmm_score(scdrs_ctx* c) {
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
     const int acc_stride = (ncol + 15) & ~15;
-    const size_t per_warp = (size_t)acc_stride * sizeof(double);
+    const size_t per_warp = (size_t)acc_stride * sizeof(double);          // one cell's accumulators
     SCDRS_CHECK(per_warp <= 200 * 1024, "1 + n_ctrl = %d needs more shared memory than one SM has", ncol);
     int wpb = (int)((72 * 1024) / per_warp);
     if (wpb > 8) wpb = 8;
