@@ -49,12 +49,14 @@ class _GeneBins:
 
 
 def _bins_for(df_gene, ctrl_match_key, n_genebin, cache=None):
+    """Bins for one match key, cached per data set under a content hash of the key column."""
     if cache is None:
         return _GeneBins(df_gene, ctrl_match_key, n_genebin)
     h = pd.util.hash_pandas_object(df_gene[ctrl_match_key], index=True).values.sum()
-    ck = (ctrl_match_key, n_genebin, df_gene.shape[0], int(h))
+    ck = ("bins", ctrl_match_key, n_genebin, df_gene.shape[0], int(h))
     if ck not in cache:
-        cache.clear()
+        for old in [k_ for k_ in cache if isinstance(k_, tuple) and k_[0] == "bins"]:
+            del cache[old]
         cache[ck] = _GeneBins(df_gene, ctrl_match_key, n_genebin)
     return cache[ck]
 
@@ -157,42 +159,63 @@ def score_cell(
     return _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score)
 
 
-def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed):
-    """Host work of one trait: gene intersection (:146-159) and control draws (:168)."""
-    param = adata.uns["SCDRS_PARAM"]
-    cache = state.bins_cache if state is not None else None
-    ck = ("df_gene", id(param["GENE_STATS"]), id(adata.var_names), param["GENE_STATS"].shape)
-    if cache is not None and ck in cache:
-        df_gene, col_of = cache[ck]
-    else:
+class _GeneTable:
+    """Per-dataset lookup tables derived from GENE_STATS / var_names (scdrs/method.py:146-148)."""
+
+    def __init__(self, adata):
+        param = adata.uns["SCDRS_PARAM"]
         df_gene = param["GENE_STATS"].loc[adata.var_names].copy()       # :146
         df_gene["gene"] = df_gene.index
         df_gene.drop_duplicates(subset="gene", inplace=True)            # :148
-        col_of = pd.Index(adata.var_names).get_indexer(df_gene["gene"].values).astype(np.int64)
-        if cache is not None:
-            for k_ in [k_ for k_ in cache if isinstance(k_, tuple) and k_[0] == "df_gene"]:
-                del cache[k_]
-            cache[ck] = (df_gene, col_of)
+        names = [str(x) for x in df_gene["gene"].values]
+        self.df_gene = df_gene
+        self.col_of = pd.Index(adata.var_names).get_indexer(df_gene["gene"].values).astype(np.int64)
+        self.pos_of = {g: i for i, g in enumerate(names)}
+        n_gene = adata.shape[1]
+        self.var = np.zeros(n_gene)
+        self.var_tech = np.zeros(n_gene)
+        self.var[self.col_of] = df_gene["var"].values.astype(np.float64)
+        self.var_tech[self.col_of] = df_gene["var_tech"].values.astype(np.float64)
+        self.stamp = _gene_table_stamp(adata)
 
+
+def _gene_table_stamp(adata):
+    """Cheap content stamp: users do edit GENE_STATS in place (docs/faq.rst:84-87 of the reference)."""
+    gs = adata.uns["SCDRS_PARAM"]["GENE_STATS"]
+    return (id(gs), len(adata.var_names), gs.shape, tuple(gs.columns),
+            int(pd.util.hash_pandas_object(gs, index=True).values.sum()))
+
+
+def _gene_table(adata, state):
+    cache = state.bins_cache if state is not None else None
+    if cache is not None:
+        tab = cache.get("gene_table")
+        if tab is not None and tab.stamp == _gene_table_stamp(adata):
+            return tab
+    tab = _GeneTable(adata)
+    if cache is not None:
+        cache["gene_table"] = tab
+    return tab
+
+
+def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed,
+                   tab=None, bins=None):
+    """Host work of one trait: gene intersection (:146-159) and control draws (:168).
+
+    ``tab`` / ``bins`` let a multi-trait caller compute the per-dataset tables once."""
+    if tab is None:
+        tab = _gene_table(adata, state)
     gene_list = list(gene_list)
     gene_weight = list(gene_weight) if gene_weight is not None else [1] * len(gene_list)
     dic_gene_weight = {x: y for x, y in zip(gene_list, gene_weight)}    # :157
-    pos_index = pd.Index(df_gene["gene"].values)
-    genes = sorted(set(gene_list) & set(pos_index))                     # :158
-    trait_pos = pos_index.get_indexer(genes).astype(np.int64)
+    genes = sorted(g for g in dic_gene_weight if g in tab.pos_of)       # :158 sorted(set & set)
+    trait_pos = np.fromiter((tab.pos_of[g] for g in genes), dtype=np.int64, count=len(genes))
     trait_gw = np.array([dic_gene_weight[x] for x in genes], dtype=np.float64)
-
-    bins = _bins_for(df_gene, ctrl_match_key, n_genebin, cache)
-    ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=col_of)
-
-    # gene statistics aligned to the columns of X
-    n_gene = adata.shape[1]
-    var = np.zeros(n_gene)
-    var_tech = np.zeros(n_gene)
-    var[col_of] = df_gene["var"].values.astype(np.float64)
-    var_tech[col_of] = df_gene["var_tech"].values.astype(np.float64)
-    return dict(genes=genes, trait_cols=col_of[trait_pos].astype(np.int32), trait_gw=trait_gw,
-                ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=var, var_tech=var_tech)
+    if bins is None:
+        bins = _bins_for(tab.df_gene, ctrl_match_key, n_genebin, state.bins_cache if state is not None else None)
+    ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=tab.col_of)
+    return dict(genes=genes, trait_cols=tab.col_of[trait_pos].astype(np.int32), trait_gw=trait_gw,
+                ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=tab.var, var_tech=tab.var_tech)
 
 
 def _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score):
@@ -365,9 +388,11 @@ def score_traits(
     traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
     if not traits:
         return {} if on_result is None else []
-    # warm the per-dataset caches (df_gene, bins) once, outside the pool
+    # per-dataset tables once, outside the pool
+    tab = _gene_table(adata, state)
+    bins = _GeneBins(tab.df_gene, ctrl_match_key, n_genebin)
     first = _prepare_trait(adata, state, dict_gs[traits[0]][0], dict_gs[traits[0]][1], ctrl_match_key,
-                           n_ctrl, n_genebin, random_seed)
+                           n_ctrl, n_genebin, random_seed, tab=tab, bins=bins)
     ctx.set_gene_stats(first["var"], first["var_tech"])
     n_jobs = n_jobs or max(1, min(len(traits), (os.cpu_count() or 2) - 1, 16))
     results = {}
@@ -375,7 +400,8 @@ def score_traits(
         futs = {traits[0]: None}
         for t in traits[1:]:
             g, w = dict_gs[t]
-            futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed)
+            futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
+                                  tab, bins)
         for t in traits:
             prep = first if futs[t] is None else futs[t].result()
             futs[t] = None
