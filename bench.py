@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--density", type=float, default=0.10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-cells", type=int, default=10000)
+    ap.add_argument("--cpu-sample-cells", type=int, default=30000)
     ap.add_argument("--cpu-sample-traits", type=int, default=2)
     return ap.parse_args()
 

@@ -132,9 +132,24 @@ __global__ void w_padded_len_kernel(int n_gene, const uint32_t* __restrict__ cnt
     if (g == n_gene) plen[g] = 0;
 }
 
-__global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, uint32_t* __restrict__ meta) {
+// per gene, fetched with ONE 16-byte load per stored entry of X: the base weight folded into the
+// expression value and the packed location of the gene's set-id list
+struct __align__(16) GeneInfo {
+    double base;
+    uint32_t meta;   // (first 16-slot group << 12) | number of groups
+    uint32_t pad;
+};
+
+__global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, const double* __restrict__ gbase,
+                              GeneInfo* __restrict__ info) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_gene) meta[g] = ((p_ptr[g] >> 4) << 12) | ((p_ptr[g + 1] - p_ptr[g]) >> 4);
+    if (g < n_gene) {
+        GeneInfo gi;
+        gi.base = gbase[g];
+        gi.meta = ((p_ptr[g] >> 4) << 12) | ((p_ptr[g + 1] - p_ptr[g]) >> 4);
+        gi.pad = 0;
+        info[g] = gi;
+    }
 }
 
 __global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t* __restrict__ set_genes,
@@ -255,7 +270,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_TRY(c->w_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->w_cursor.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
-    SCDRS_TRY(c->p_meta.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+    SCDRS_TRY(c->p_meta.reserve((size_t)(n_gene + 1) * sizeof(GeneInfo)));
     SCDRS_CHECK(n_entry + 16 * (int64_t)n_gene < ((int64_t)1 << 24), "gene-set lists too large for the packed index");
     SCDRS_CHECK(ncol <= 4095 * 16, "too many gene sets");
     SCDRS_TRY(c->w_col.reserve(n_entry * sizeof(uint16_t)));
@@ -293,8 +308,8 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                                                      c->p_ptr.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     SCDRS_TRY(exclusive_scan_u32(c, c->p_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), n_gene + 1));
-    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(),
-                                                               c->p_meta.as<uint32_t>());
+    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
+                                                               c->p_meta.as<GeneInfo>());
     SCDRS_LAUNCH_CHECK(c);
     SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
     w_fill_kernel<<<nb, 256, 0, c->stream>>>(n_entry, n_s, n_sc > 0 ? n_sc : 1, c->set_genes.as<int32_t>(),
@@ -434,8 +449,8 @@ template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                  const float* __restrict__ data, const double* __restrict__ gbase,
-                  const uint32_t* __restrict__ p_meta, const uint16_t* __restrict__ p_col,
+                  const float* __restrict__ data, const GeneInfo* __restrict__ ginfo,
+                  const uint16_t* __restrict__ p_col,
                   const float* __restrict__ p_val, const double* __restrict__ colscale, int k,
                   const double* __restrict__ cov_mat, const double* __restrict__ covM,
                   const double* __restrict__ covm, float* __restrict__ dev_mat,
@@ -455,9 +470,9 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
             uint32_t meta = 0;
             double xd = 0.0;
             if (q < p1) {
-                const int g = indices[q];
-                xd = (double)data[q] * gbase[g];
-                meta = p_meta[g];
+                const int4 gi = __ldg(reinterpret_cast<const int4*>(ginfo + indices[q]));
+                xd = (double)data[q] * __hiloint2double(gi.y, gi.x);
+                meta = (uint32_t)gi.z;
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
             // software pipeline, two entries deep: while entry i is applied, the set ids of entries
@@ -546,14 +561,14 @@ int spmm_score(scdrs_ctx* c) {
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (c->w_binary)
         spmm_score_kernel<false><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->gbase.as<double>(),
-            c->p_meta.as<uint32_t>(), c->p_col.as<uint16_t>(), nullptr, c->colscale.as<double>(), c->k,
+            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
+            c->p_col.as<uint16_t>(), nullptr, c->colscale.as<double>(), c->k,
             c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->dev_mat.as<float>(),
             c->row_ref.as<double>());
     else
         spmm_score_kernel<true><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->gbase.as<double>(),
-            c->p_meta.as<uint32_t>(), c->p_col.as<uint16_t>(), c->p_val.as<float>(), c->colscale.as<double>(),
+            c->n_cell, ncol, c->ld, acc_stride, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
+            c->p_col.as<uint16_t>(), c->p_val.as<float>(), c->colscale.as<double>(),
             c->k, c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(),
             c->dev_mat.as<float>(), c->row_ref.as<double>());
     SCDRS_LAUNCH_CHECK(c);
