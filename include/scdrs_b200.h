@@ -129,6 +129,11 @@ int scdrs_gene_cell_stats(scdrs_ctx* ctx, int32_t transform, const double* cell_
                           int32_t center, double denom, double* gene_sum, double* gene_sumsq,
                           double* cell_sum, double* cell_sumsq);
 
+/* Gene means and C^T X for the covariate regression of pp.preprocess (scdrs/pp.py:206, :209-212).
+ * cov_mat[n_cell x k] (host f64, k <= 16).  Outputs (host): gene_mean[n_gene] f32 = X.mean(axis=0)
+ * with scipy's float32 operation order; xtc[n_gene x k] f64 = (C^T X)^T accumulated in cell order. */
+int scdrs_gene_mean_xtc(scdrs_ctx* ctx, int32_t k, const double* cov_mat, float* gene_mean, double* xtc);
+
 /* ---- host code: the random draws of _select_ctrl_geneset (scdrs/method.py:276, 295-307) --------
  * numpy-legacy MT19937 seeded with `seed`, bins visited in the given order; for every bin b with
  * bin_ntrait[b] > 0 and every control set i: permutation(len(bin b))[:bin_ntrait[b]] indexes

@@ -50,6 +50,7 @@ SIGNATURES = {
     "scdrs_empi_null_count_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_mean_xtc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p]),
 }
@@ -242,6 +243,15 @@ class Context:
         fn = self._L.scdrs_empi_null_count_f32 if f32 else self._L.scdrs_empi_null_count_f64
         check(fn(self._h, v_t.shape[0], ptr(v_t), v_null.shape[0], ptr(v_null), ptr(out)))
         return out
+
+    def gene_mean_xtc(self, cov_mat):
+        """(X.mean(axis=0) as float32, (C^T X)^T as float64 [n_gene x k])."""
+        cov_mat = as_c(cov_mat, np.float64)
+        k = cov_mat.shape[1]
+        gm = np.empty(self.n_gene, np.float32)
+        xtc = np.empty((self.n_gene, k), np.float64)
+        check(self._L.scdrs_gene_mean_xtc(self._h, k, ptr(cov_mat), ptr(gm), ptr(xtc)))
+        return gm, xtc
 
     def gene_cell_stats(self, transform, cell_weight=None, want_gene=True, want_cell=True, center=False, denom=0.0):
         w = None if cell_weight is None else as_c(cell_weight, np.float64)

@@ -469,4 +469,23 @@ int scdrs_gene_cell_stats(scdrs_ctx* c, int32_t transform, const double* cell_we
     return rc;
 }
 
+int scdrs_gene_mean_xtc(scdrs_ctx* c, int32_t k, const double* cov_mat, float* gene_mean, double* xtc) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    SCDRS_CHECK(gene_mean != nullptr && (k == 0 || (cov_mat != nullptr && xtc != nullptr)), "null pointer");
+    const int64_t n = c->n_cell;
+    const int g = c->n_gene;
+    DevBuf d_cov;
+    SCDRS_TRY(h2d(c, d_cov, cov_mat, (size_t)n * k * sizeof(double)));
+    SCDRS_TRY(c->stage.reserve((size_t)g * sizeof(float) + (size_t)g * (k > 0 ? k : 1) * sizeof(double) + 64));
+    double* d_xtc = c->stage.as<double>();
+    float* d_gm = reinterpret_cast<float*>(d_xtc + (size_t)g * (k > 0 ? k : 1));
+    int rc = gene_mean_xtc(c, k, d_cov.as<double>(), d_gm, d_xtc);
+    if (rc == 0) rc = d2h(c, gene_mean, d_gm, (size_t)g * sizeof(float));
+    if (rc == 0 && k > 0) rc = d2h(c, xtc, d_xtc, (size_t)g * k * sizeof(double));
+    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("stream sync failed"); rc = 1; }
+    d_cov.release();
+    return rc;
+}
+
 }  // extern "C"

@@ -128,6 +128,8 @@ int null_count_generic_f64(scdrs_ctx* c, int64_t n_t, const double* dev_t, int64
 int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, int center, double denom,
                     double* dev_gsum, double* dev_gsumsq, double* dev_csum, double* dev_csumsq);
 
+int gene_mean_xtc(scdrs_ctx* c, int k, const double* dev_cov, float* dev_gmean32, double* dev_xtc);
+
 // ---- scan (empi_null.cu) --------------------------------------------------------------------
 int exclusive_scan_u32(scdrs_ctx* c, const uint32_t* in, uint32_t* out, int64_t n);
 int exclusive_scan_u64(scdrs_ctx* c, const unsigned long long* in, unsigned long long* out,

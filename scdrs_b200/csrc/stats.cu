@@ -106,6 +106,78 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
     }
 }
 
+// ---- gene means and C^T X for the covariate regression (scdrs/pp.py:206, :209-212) --------------
+// Same tiling as above.  The reference's `X.mean(axis=0)` on float32 CSR data multiplies every stored
+// value by float32(1/n) and accumulates in float32 in cell order (scipy csc_matvec); that sum is
+// reproduced operation by operation so COV_GENE_MEAN carries the same bits.  C^T X is accumulated
+// in float64 in cell order (multiply, then add), as scipy's csc_matvecs does.
+constexpr int kMaxCovReg = 16;
+
+__global__ void __launch_bounds__(kGeneTile)
+gene_mean_xtc_kernel(int64_t n_cell, int n_gene, int k, float inv_n,
+                     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                     const float* __restrict__ data, const double* __restrict__ cov_mat,
+                     float* __restrict__ gmean32, double* __restrict__ xtc) {
+    __shared__ float tile[kRowTile][kGeneTile + 1];
+    const int g0 = blockIdx.x * kGeneTile;
+    const int g = g0 + threadIdx.x;
+    const bool ok = g < n_gene;
+    float s32 = 0.f;
+    double acc[kMaxCovReg];
+#pragma unroll
+    for (int kk = 0; kk < kMaxCovReg; ++kk) acc[kk] = 0.0;
+    for (int64_t r0 = 0; r0 < n_cell; r0 += kRowTile) {
+        const int nr = (int)((n_cell - r0) < kRowTile ? (n_cell - r0) : kRowTile);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kRowTile * (kGeneTile + 1); i += kGeneTile) (&tile[0][0])[i] = 0.f;
+        __syncthreads();
+        if ((int)threadIdx.x < nr) {
+            const int64_t p0 = indptr[r0 + threadIdx.x], p1 = indptr[r0 + threadIdx.x + 1];
+            int64_t lo = p0, hi = p1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (indices[mid] < g0) lo = mid + 1; else hi = mid;
+            }
+            for (int64_t t = lo; t < p1; ++t) {
+                const int col = indices[t] - g0;
+                if (col >= kGeneTile) break;
+                tile[threadIdx.x][col] = data[t];
+            }
+        }
+        __syncthreads();
+        if (ok) {
+            for (int r = 0; r < nr; ++r) {
+                const float x = tile[r][threadIdx.x];
+                if (x != 0.f) {      // only stored entries take part, as in the sparse products
+                    s32 = __fadd_rn(s32, __fmul_rn(x, inv_n));
+                    const double xd = (double)x;
+                    const double* crow = cov_mat + (r0 + r) * k;
+#pragma unroll
+                    for (int kk = 0; kk < kMaxCovReg; ++kk)
+                        if (kk < k) acc[kk] = __dadd_rn(acc[kk], __dmul_rn(xd, crow[kk]));
+                }
+            }
+        }
+    }
+    if (ok) {
+        gmean32[g] = s32;
+#pragma unroll
+        for (int kk = 0; kk < kMaxCovReg; ++kk)
+            if (kk < k) xtc[(size_t)g * k + kk] = acc[kk];
+    }
+}
+
+int gene_mean_xtc(scdrs_ctx* c, int k, const double* dev_cov, float* dev_gmean32, double* dev_xtc) {
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set (call scdrs_set_csr_* first)");
+    SCDRS_CHECK(k >= 0 && k <= kMaxCovReg, "this kernel handles at most %d covariates (got %d)", kMaxCovReg, k);
+    const int tiles = (c->n_gene + kGeneTile - 1) / kGeneTile;
+    gene_mean_xtc_kernel<<<tiles, kGeneTile, 0, c->stream>>>(
+        c->n_cell, c->n_gene, k, (float)(1.0 / (double)c->n_cell), c->indptr, c->indices, c->data, dev_cov,
+        dev_gmean32, dev_xtc);
+    SCDRS_LAUNCH_CHECK(c);
+    return 0;
+}
+
 // ---- sparse part of the per-cell statistics: one warp per cell ----------------------------------
 template <int TRANSFORM>
 __global__ void __launch_bounds__(256)

@@ -81,7 +81,7 @@ def preprocess(data, cov=None, adj_prop=None, n_mean_bin=20, n_var_bin=20, n_chu
 
     if flag_cov:
         assert (
-            len(set(cov.index) & set(adata.obs_names)) > 0.75 * n_cell
+            len(pd.Index(cov.index).intersection(pd.Index(adata.obs_names))) > 0.75 * n_cell
         ), "cov does not match the cells in data"
         df_cov = pd.DataFrame(index=adata.obs_names)
         df_cov = df_cov.join(cov)
@@ -91,11 +91,18 @@ def preprocess(data, cov=None, adj_prop=None, n_mean_bin=20, n_var_bin=20, n_chu
         if (v_resid ** 2).mean() > 0.01:                                # :201-203
             df_cov["SCDRS_CONST"] = 1
         cov_values = df_cov.values.astype(np.float64)
-        v_gene_mean = np.array(adata.X.mean(axis=0)).flatten()          # :206
+        if flag_sparse and adata.X.dtype == np.float32 and cov_values.shape[1] <= 16:
+            # gene means and C^T X in one device pass over X, in scipy's own operation order
+            ctx = get_state(adata).ensure_matrix(adata)
+            v_gene_mean, xtc = ctx.gene_mean_xtc(cov_values)
+            mat_xtc = xtc.T
+        else:
+            v_gene_mean = np.array(adata.X.mean(axis=0)).flatten()      # :206
+            mat_xtc = np.asarray((adata.X.T @ cov_values).T) if flag_sparse else None
         if flag_sparse:
             mat_beta = np.linalg.solve(                                 # :209-212
                 cov_values.T @ cov_values / n_cell,
-                np.asarray((adata.X.T @ cov_values).T) / n_cell,
+                mat_xtc / n_cell,
             )
             adata.uns["SCDRS_PARAM"]["COV_MAT"] = df_cov
             adata.uns["SCDRS_PARAM"]["COV_BETA"] = pd.DataFrame(

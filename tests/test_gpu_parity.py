@@ -275,6 +275,8 @@ def test_preprocess_matches_reference_golden_stats(sc, path):
     assert np.allclose(param["CELL_STATS"]["var"].values.astype(float), z["cs_var"], rtol=1e-4, atol=1e-9)
     if case["use_cov"]:
         assert np.allclose(param["COV_BETA"].values, z["cov_beta"], rtol=1e-9, atol=1e-12)
+        # float32 gene means in scipy's own operation order: identical bits
+        assert np.array_equal(param["COV_GENE_MEAN"].values.astype(np.float64), z["cov_gene_mean"])
 
 
 def test_compute_stats_modes_agree(sc):
@@ -431,3 +433,61 @@ def test_full_size_config2_properties(sc, ctx):
     # idempotence / bitwise reproducibility of the whole device path
     df2 = sc.score_cell(adata, genes, gene_weight=w, n_ctrl=1000, return_ctrl_norm_score=True)
     assert np.array_equal(df.values, df2.values)
+
+
+def test_get_mean_var_matches_numpy(sc):
+    """_get_mean_var / _get_mean_var_implicit_cov_corr (tests/test_pp.py:384-458, tests/test_pp_adj_prop.py:246-457)."""
+    from scdrs_b200 import pp, synth
+    from scdrs_b200.anndata_lite import AnnData
+
+    rng = np.random.default_rng(3)
+    X = synth.make_csr(400, 300, density=0.2, seed=4)
+    D = X.toarray().astype(np.float64)
+    w = rng.uniform(0.5, 2.0, size=400)
+    for axis in (0, 1):
+        m, v = pp._get_mean_var(X, axis=axis)
+        assert np.allclose(m, D.mean(axis=axis), rtol=1e-6) and np.allclose(v, D.var(axis=axis), rtol=1e-5, atol=1e-9)
+        m, v = pp._get_mean_var(D, axis=axis)
+        assert np.allclose(m, D.mean(axis=axis), rtol=1e-6) and np.allclose(v, D.var(axis=axis), rtol=1e-5, atol=1e-9)
+    m, v = pp._get_mean_var(X, axis=0, weights=w)
+    wm = np.average(D, axis=0, weights=w)
+    assert np.allclose(m, wm, rtol=1e-6) and np.allclose(v, np.average(D * D, axis=0, weights=w) - wm ** 2, rtol=1e-5, atol=1e-9)
+    # implicit covariate correction with a random beta (tests/test_pp.py:419-458)
+    adata = AnnData(X)
+    cov = pd.DataFrame({"const": 1.0, "c1": rng.normal(size=400)}, index=adata.obs_names)
+    beta = pd.DataFrame(rng.normal(size=(300, 2)) * 0.1, index=adata.var_names, columns=cov.columns)
+    mu = pd.Series(rng.uniform(0, 1, size=300), index=adata.var_names)
+    adata.uns["SCDRS_PARAM"] = {"FLAG_SPARSE": True, "FLAG_COV": True, "COV_MAT": cov, "COV_BETA": beta, "COV_GENE_MEAN": mu}
+    T = D + cov.values @ beta.values.T + mu.values
+    for axis in (0, 1):
+        m, v = pp._get_mean_var_implicit_cov_corr(adata, axis=axis)
+        assert np.allclose(m, T.mean(axis=axis), rtol=1e-8) and np.allclose(v, T.var(axis=axis), rtol=1e-6, atol=1e-10)
+    m, v = pp._get_mean_var_implicit_cov_corr(adata, axis=0, transform_func=np.expm1)
+    E = np.expm1(T)
+    assert np.allclose(m, E.mean(axis=0), rtol=1e-8) and np.allclose(v, E.var(axis=0), rtol=1e-6)
+    m, v = pp._get_mean_var_implicit_cov_corr(adata, axis=0, weights=w)
+    wm = np.average(T, axis=0, weights=w)
+    assert np.allclose(m, wm, rtol=1e-8) and np.allclose(v, np.average(T * T, axis=0, weights=w) - wm ** 2, rtol=1e-6, atol=1e-10)
+
+
+def test_preprocess_param_schema_four_modes(sc):
+    """SCDRS_PARAM keys and flags for sparse/dense x cov/nocov (tests/test_pp.py:10-112)."""
+    from scdrs_b200 import synth
+
+    for dense in (False, True):
+        for use_cov in (False, True):
+            adata, cov = synth.make_adata(300, 400, density=0.2, seed=2)
+            if dense:
+                adata.X = adata.X.toarray()
+            sc.preprocess(adata, cov=cov if use_cov else None)
+            p = adata.uns["SCDRS_PARAM"]
+            assert p["FLAG_SPARSE"] == (not dense) and p["FLAG_COV"] == use_cov and p["FLAG_ADJ_PROP"] is False
+            assert ("COV_MAT" in p) == (use_cov and not dense) and ("COV_BETA" in p) == (use_cov and not dense)
+            assert list(p["CELL_STATS"].columns) == ["mean", "var"] and p["GENE_STATS"].shape == (400, 7)
+            if use_cov and not dense:
+                assert p["COV_BETA"].shape == (400, 4) and p["COV_GENE_MEAN"].shape == (400,)
+    adata, cov = synth.make_adata(300, 400, density=0.2, seed=2)
+    with pytest.raises(AssertionError, match="cov does not match"):
+        sc.preprocess(adata, cov=cov.set_index(pd.Index(["x%d" % i for i in range(300)])))
+    with pytest.raises(AssertionError, match="adj_prop"):
+        sc.preprocess(adata, adj_prop="nope")

@@ -187,3 +187,28 @@ def test_cli_flag_parsing():
         cli.main(["munge-gs", "--out-file", "x"])
     with pytest.raises(ValueError):
         cli.compute_score("a", "mouse", "g", "mouse", "o", ctrl_match_opt="bad")
+
+
+def test_reg_out_matches_lstsq():
+    # tests/test_pp.py:344-381 of the reference
+    from scdrs_b200 import pp
+
+    rng = np.random.default_rng(0)
+    X = np.column_stack([np.ones(200), rng.normal(size=(200, 3))])
+    Y = rng.normal(size=(200, 7))
+    want = Y - X @ np.linalg.lstsq(X, Y, rcond=None)[0]
+    assert np.allclose(pp.reg_out(Y, X), want)
+    assert np.allclose(pp.reg_out(Y[:, 0], X), want[:, 0])
+    from scipy import sparse
+    assert np.allclose(pp.reg_out(sparse.csr_matrix(Y), sparse.csr_matrix(X)), want)
+
+
+def test_category2dummy():
+    from scdrs_b200 import pp
+
+    df = pd.DataFrame({"a": [1.0, 2.0, 3.0, 4.0], "sex": ["m", "f", None, "m"], "b": ["x", "y", "z", "x"]})
+    out = pp.category2dummy(df)
+    assert list(out.columns) == ["a", "sex_m", "b_y", "b_z"]
+    assert np.isnan(out.loc[2, "sex_m"]) and out.loc[0, "sex_m"] == 1 and out.loc[1, "sex_m"] == 0
+    with pytest.raises(AssertionError):
+        pp.category2dummy(df, cols=["nope"])
