@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--n-trait-gene", type=int, default=1000)
     ap.add_argument("--n-ctrl", type=int, default=1000)
     ap.add_argument("--density", type=float, default=0.10)
+    ap.add_argument("--weighted", action="store_true", help="MAGMA-z-like gene weights (BASELINE configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=30000)
@@ -115,7 +116,7 @@ def build_workload(args, rank, device):
     scdrs_b200.preprocess(adata, cov=cov)
     t_pp = time.time() - t0
     traits = synth.make_traits(adata.var_names, n_trait=args.n_trait, n_gene_per_trait=args.n_trait_gene,
-                               weighted=False, seed=1000)
+                               weighted=bool(getattr(args, "weighted", False)), seed=1000)
     return adata, traits, dict(generate_s=round(t_gen, 2), preprocess_s=round(t_pp, 2), nnz=int(X.nnz))
 
 
@@ -285,9 +286,10 @@ def reference_arm(args):
 def workload_config(args, n_gpus):
     return {
         "workload": "TMS-FACS-shaped synthetic (BASELINE configs[1]): %d cells x %d genes per GPU, %.0f%% nnz, "
-                    "%d binary %d-gene traits, 4 covariates (implicit covariate correction), n_ctrl=%d, "
+                    "%d %s %d-gene traits, 4 covariates (implicit covariate correction), n_ctrl=%d, "
                     "weight_opt=vs, ctrl_match_key=mean_var" % (args.n_cell, args.n_gene, 100 * args.density,
-                                                               args.n_trait, args.n_trait_gene, args.n_ctrl),
+                                                               args.n_trait, "weighted" if getattr(args, "weighted", False) else "binary",
+                                                               args.n_trait_gene, args.n_ctrl),
         "n_cell_per_gpu": args.n_cell, "n_gene": args.n_gene, "n_trait": args.n_trait, "n_ctrl": args.n_ctrl,
         "sharding": "cells across %d GPU(s); pooled null over all cells" % n_gpus,
         "l2": "inputs larger than L2 (X is %.2f GB per GPU, re-read for every trait)" % (

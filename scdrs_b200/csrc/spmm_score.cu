@@ -541,9 +541,17 @@ int spmm_score(scdrs_ctx* c) {
     const int acc_stride = (ncol + 15) & ~15;
     const size_t per_warp = (size_t)acc_stride * sizeof(double);          // one cell's accumulators
     SCDRS_CHECK(per_warp <= 200 * 1024, "1 + n_ctrl = %d needs more shared memory than one SM has", ncol);
-    int wpb = (int)((72 * 1024) / per_warp);
-    if (wpb > 8) wpb = 8;
-    if (wpb < 1) wpb = 1;
+    // warps per block / blocks per SM that keep the most cells in flight within 227 KB of shared
+    // memory per SM (each resident block also costs 1 KB of reserved shared memory)
+    int wpb = 1, per_sm = 1, best = 0;
+    for (int w = 1; w <= 8; ++w) {
+        const size_t blk = per_warp * w + 1024;
+        if (per_warp * w > 200 * 1024) break;
+        int b = (int)((227 * 1024) / blk);
+        if (b > 32) b = 32;
+        if (b * w > 64) b = 64 / w;
+        if (b >= 1 && b * w >= best) { best = b * w; wpb = w; per_sm = b; }
+    }
     const size_t smem = per_warp * wpb;
     static bool attr_set = false;
     if (!attr_set) {
@@ -551,9 +559,6 @@ int spmm_score(scdrs_ctx* c) {
         SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    int per_sm = (int)((226 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm * wpb > 64) per_sm = 64 / wpb;
     int64_t grid = (int64_t)kNumSM * per_sm;
     const int64_t need = (c->n_cell + wpb - 1) / wpb;
     if (grid > need) grid = need;
