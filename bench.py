@@ -332,7 +332,13 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # ---- control sets drawn once (host), as inputs of the device-resident leg
-    preps = [M._prepare_trait(adata, state, traits[t][0], traits[t][1], "mean_var", n_ctrl, 200, 0) for t in names]
+    from concurrent.futures import ThreadPoolExecutor
+
+    tab = M._gene_table(adata, state)
+    bins = M._GeneBins(tab.df_gene, "mean_var", 200)
+    with ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1))) as pool:
+        preps = list(pool.map(lambda t: M._prepare_trait(adata, state, traits[t][0], traits[t][1], "mean_var",
+                                                         n_ctrl, 200, 0, tab, bins), names))
     ctx.set_gene_stats(preps[0]["var"], preps[0]["var_tech"])
 
     if world > 1:
