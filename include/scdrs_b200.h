@@ -142,6 +142,16 @@ int scdrs_gene_mean_xtc(scdrs_ctx* ctx, int32_t k, const double* cov_mat, float*
 int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr, const int32_t* bin_genes,
                       const int32_t* bin_ntrait, int32_t n_ctrl, int32_t n_s, int32_t* ctrl_genes);
 
+/* ---- host code: score-file writer (bin/scdrs:276-288; format docs/file_format.rst:81-108) --------
+ * Gzip TSV: `header` (one line, '\n'-terminated), then per row: name, then n_col float32 fields in
+ * pandas' to_csv text (shortest round-trip; NaN -> empty).  names/name_off: concatenated UTF-8 row
+ * names and their n_row + 1 offsets.  Row blocks are formatted and deflated by n_thread threads. */
+int scdrs_write_score_gz(const char* path, const char* header, int64_t n_row, int32_t n_col,
+                         const char* names, const int64_t* name_off, const float* values,
+                         int32_t n_thread, int32_t level);
+/* one float32 in that text format into out64 (NUL-terminated); returns its length */
+int scdrs_format_f32(float v, char* out64);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ SIGNATURES = {
     "scdrs_gene_mean_xtc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p]),
+    "scdrs_write_score_gz": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_int32]),
+    "scdrs_format_f32": (C.c_int, [C.c_float, C.c_char_p]),
 }
 
 WEIGHT_OPT = {"uniform": 0, "vs": 1, "inv_std": 2}
@@ -272,3 +275,25 @@ def select_ctrl(seed, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s):
     check(lib().scdrs_select_ctrl(int(seed) & 0xFFFFFFFF, bin_ntrait.shape[0], ptr(bin_ptr), ptr(bin_genes),
                                   ptr(bin_ntrait), int(n_ctrl), int(n_s), ptr(out)))
     return out
+
+
+def write_score_gz(path, df, n_thread=None, level=6):
+    """Write a float32 DataFrame as the gzip TSV ``DataFrame.to_csv(path, sep="\\t", compression="gzip")`` gives."""
+    import os
+
+    values = as_c(df.values, np.float32)
+    names = [str(x).encode("utf-8") for x in df.index]
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in names], out=off[1:])
+    blob = b"".join(names)
+    header = "\t".join([df.index.name or ""] + [str(c) for c in df.columns]) + "\n"
+    n_thread = n_thread or max(1, min(32, (os.cpu_count() or 2)))
+    buf = C.create_string_buffer(blob, len(blob) + 1)
+    check(lib().scdrs_write_score_gz(os.fsencode(path), header.encode("utf-8"), values.shape[0], values.shape[1],
+                                     C.cast(buf, C.c_void_p), ptr(off), ptr(values), int(n_thread), int(level)))
+
+
+def format_f32(v):
+    buf = C.create_string_buffer(64)
+    n = lib().scdrs_format_f32(float(np.float32(v)), buf)
+    return buf.raw[:n].decode()

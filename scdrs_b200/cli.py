@@ -154,11 +154,11 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
                   % (trait, len(dict_gs[trait][0]), time.time() - sys_start_time))
 
     def write(trait, df_res):
-        df_res.iloc[:, 0:6].to_csv(os.path.join(out_folder, "%s.score.gz" % trait), sep="\t", index=True,
-                                   compression="gzip")
+        # same bytes (after gunzip) as DataFrame.to_csv(sep="\t", compression="gzip"), written by the
+        # multi-threaded formatter/deflater of libscdrs_b200 (bin/scdrs:276-288 of the reference)
+        util.write_score_file(os.path.join(out_folder, "%s.score.gz" % trait), df_res.iloc[:, 0:6])
         if flag_return_ctrl_raw_score | flag_return_ctrl_norm_score:
-            df_res.to_csv(os.path.join(out_folder, "%s.full_score.gz" % trait), sep="\t", index=True,
-                          compression="gzip")
+            util.write_score_file(os.path.join(out_folder, "%s.full_score.gz" % trait), df_res)
         v_fdr = util.fdr_bh(df_res["pval"].values)
         print("Trait=%s, n_gene=%d: %d/%d FDR<0.1 cells, %d/%d FDR<0.2 cells (sys_time=%0.1fs)"
               % (trait, len(dict_gs[trait][0]), (v_fdr < 0.1).sum(), df_res.shape[0], (v_fdr < 0.2).sum(),

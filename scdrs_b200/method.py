@@ -402,16 +402,26 @@ def score_traits(
             g, w = dict_gs[t]
             futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
                                   tab, bins)
+        pending = []          # (trait, future of the result frame): frames are built off the critical path
+
+        def drain(limit):
+            while len(pending) > limit:
+                t_done, fut = pending.pop(0)
+                df_done = fut.result()
+                if on_result is None:
+                    results[t_done] = df_done
+                else:
+                    on_result(t_done, df_done)
+
         for t in traits:
             prep = first if futs[t] is None else futs[t].result()
             futs[t] = None
             out = ctx.score_trait(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
                                   weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
                                   want_ctrl_norm=return_ctrl_norm_score)
-            df = _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score)
-            if on_result is None:
-                results[t] = df
-            else:
-                on_result(t, df)
+            pending.append((t, pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
+                                           return_ctrl_norm_score)))
+            drain(2)
+        drain(0)
     np.random.seed(random_seed)
     return results if on_result is None else traits

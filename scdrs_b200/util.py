@@ -142,6 +142,17 @@ def save_gs(gs_path: str, dict_gs: dict) -> None:
     pd.DataFrame(rows).to_csv(gs_path, sep="\t", index=False)
 
 
+def write_score_file(path, df, n_thread=None):
+    """``df.to_csv(path, sep="\\t", index=True, compression="gzip")`` for an all-float32 frame, with row blocks
+    formatted and deflated in parallel (``scdrs_write_score_gz``); other frames fall back to pandas."""
+    from . import _native
+
+    if len(df.columns) and all(dt == np.float32 for dt in df.dtypes):
+        _native.write_score_gz(path, df, n_thread=n_thread)
+    else:
+        df.to_csv(path, sep="\t", index=True, compression="gzip")
+
+
 def fdr_bh(pvals):
     """Benjamini-Hochberg adjusted p-values (what ``multipletests(method='fdr_bh')[1]`` returns;
     used only for the per-trait log line of the CLI, bin/scdrs:289-303)."""

@@ -212,3 +212,30 @@ def test_category2dummy():
     assert np.isnan(out.loc[2, "sex_m"]) and out.loc[0, "sex_m"] == 1 and out.loc[1, "sex_m"] == 0
     with pytest.raises(AssertionError):
         pp.category2dummy(df, cols=["nope"])
+
+
+def test_score_file_writer_matches_pandas_bytes(native_lib, tmp_path):
+    import gzip
+    import io
+
+    rng = np.random.default_rng(0)
+    vals = rng.normal(size=(2500, 37)) * 10.0 ** rng.integers(-8, 9, size=(2500, 37))
+    vals[0, :12] = [0.0, -0.0, np.nan, np.inf, -np.inf, 1e-4, 1e6, 999999.94, 100.0, 1e-45, 3.4028235e38, 16777216.0]
+    df = pd.DataFrame(vals.astype(np.float32), index=["cell %d" % i for i in range(2500)],
+                      columns=["raw_score"] + ["ctrl_norm_score_%d" % i for i in range(36)])
+    df.index.name = "index"
+    for nt in (1, 5):
+        path = str(tmp_path / ("s%d.gz" % nt))
+        util.write_score_file(path, df, n_thread=nt)
+        want = io.StringIO()
+        df.to_csv(want, sep="\t", index=True)
+        assert gzip.open(path, "rb").read().decode() == want.getvalue()
+    back = pd.read_csv(path, sep="\t", index_col=0)
+    assert np.array_equal(back.values.astype(np.float32), df.values, equal_nan=True)
+    # unnamed index and empty frame edge cases
+    df2 = df.iloc[:0].copy(); df2.index.name = None
+    util.write_score_file(str(tmp_path / "e.gz"), df2)
+    want = io.StringIO(); df2.to_csv(want, sep="\t", index=True)
+    assert gzip.open(str(tmp_path / "e.gz"), "rb").read().decode() == want.getvalue()
+    for v in [4.741197, 6.3260064, 0.04761905, 0.0016638935, 1e-5, 123456789.0]:
+        assert _native.format_f32(v) == str(np.float32(v))
