@@ -382,8 +382,6 @@ def score_traits(
     )
     implicit = bool(param["FLAG_SPARSE"] and param["FLAG_COV"])
     state = get_state(adata)
-    ctx = state.ensure_matrix(adata)
-    state.ensure_cov(adata, implicit)
     use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))
     traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
     if not traits:
@@ -391,17 +389,18 @@ def score_traits(
     # per-dataset tables once, outside the pool
     tab = _gene_table(adata, state)
     bins = _GeneBins(tab.df_gene, ctrl_match_key, n_genebin)
-    first = _prepare_trait(adata, state, dict_gs[traits[0]][0], dict_gs[traits[0]][1], ctrl_match_key,
-                           n_ctrl, n_genebin, random_seed, tab=tab, bins=bins)
-    ctx.set_gene_stats(first["var"], first["var_tech"])
     n_jobs = n_jobs or max(1, min(len(traits), (os.cpu_count() or 2) - 1, 16))
     results = {}
-    with ThreadPoolExecutor(max_workers=n_jobs) as pool:
-        futs = {traits[0]: None}
-        for t in traits[1:]:
+    with ThreadPoolExecutor(max_workers=n_jobs) as pool, ThreadPoolExecutor(max_workers=2) as frame_pool:
+        # the control draws of every trait start now; the upload of X overlaps with the first of them
+        futs = {}
+        for t in traits:
             g, w = dict_gs[t]
             futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
                                   tab, bins)
+        ctx = state.ensure_matrix(adata)
+        state.ensure_cov(adata, implicit)
+        ctx.set_gene_stats(tab.var, tab.var_tech)
         pending = []          # (trait, future of the result frame): frames are built off the critical path
 
         def drain(limit):
@@ -414,12 +413,11 @@ def score_traits(
                     on_result(t_done, df_done)
 
         for t in traits:
-            prep = first if futs[t] is None else futs[t].result()
-            futs[t] = None
+            prep = futs.pop(t).result()
             out = ctx.score_trait(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
                                   weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
                                   want_ctrl_norm=return_ctrl_norm_score)
-            pending.append((t, pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
+            pending.append((t, frame_pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
                                            return_ctrl_norm_score)))
             drain(2)
         drain(0)
