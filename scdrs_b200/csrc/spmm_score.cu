@@ -179,7 +179,7 @@ __global__ void w_pad_init_kernel(int64_t n_slot, uint16_t* __restrict__ col, fl
 // R = padded_length / 16, so same-pair entries land in different groups whenever there are at
 // most R of them.
 __global__ void __launch_bounds__(128)
-w_layout_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
+w_layout_deal_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
                 const uint16_t* __restrict__ w_col, const float* __restrict__ w_val,
                 uint16_t* __restrict__ p_col, float* __restrict__ p_val) {
     __shared__ uint32_t hist[4][16], run[4][16];
@@ -188,7 +188,7 @@ w_layout_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* 
     if (g >= n_gene) return;
     const uint32_t s = w_ptr[g], e = w_ptr[g + 1];
     const uint32_t ps = p_ptr[g], R = (p_ptr[g + 1] - ps) >> 4;
-    if (e == s) return;
+    if (e == s || R <= 8) return;   // short lists are placed by w_layout_greedy_kernel
     if (lane < 16) { hist[warp][lane] = 0; run[warp][lane] = 0; }
     __syncwarp();
     for (uint32_t t = s + lane; t < e; t += 32) atomicAdd(&hist[warp][w_col[t] & 15], 1u);
@@ -226,6 +226,85 @@ w_layout_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* 
             p_col[dst] = (uint16_t)col;
             if (p_val != nullptr) p_val[dst] = v;
         }
+    }
+}
+
+// One thread per gene, lists of at most 8 groups (128 entries): greedy placement that minimises the
+// number of shared-memory wavefronts, sum over groups of the largest multiplicity of a bank pair (set
+// id mod 16) inside the group.  Bank pairs are taken in order of decreasing multiplicity; every entry
+// goes to the group where it does not raise the group's maximum, then where its pair is rarest, then
+// to the emptiest group.  The list is first counting-sorted into that order in shared memory, then
+// placed in one pass; per-group state lives in registers (16 four-bit counters packed in a uint64).
+constexpr int kGreedyThreads = 64;
+constexpr int kGreedyMaxLen = 128;
+
+__global__ void __launch_bounds__(kGreedyThreads)
+w_layout_greedy_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
+                       const uint16_t* __restrict__ w_col, const float* __restrict__ w_val,
+                       uint16_t* __restrict__ p_col, float* __restrict__ p_val) {
+    extern __shared__ uint32_t stage[];   // [kGreedyMaxLen][kGreedyThreads]: (offset in list << 16) | set id
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_gene) return;
+    const uint32_t s = w_ptr[g], e = w_ptr[g + 1];
+    const uint32_t ps = p_ptr[g], R = (p_ptr[g + 1] - ps) >> 4;
+    if (e == s || R > 8) return;
+    uint32_t c[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) c[b] = 0;
+    for (uint32_t t = s; t < e; ++t) {
+        const int b = w_col[t] & 15;
+#pragma unroll
+        for (int bb = 0; bb < 16; ++bb) c[bb] += (bb == b);
+    }
+    // start[b] = number of entries whose pair comes before b in (multiplicity desc, pair asc) order
+    uint32_t start[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+            if (c[o] > c[b] || (c[o] == c[b] && o < b)) acc += c[o];
+        start[b] = acc;
+    }
+    for (uint32_t t = s; t < e; ++t) {
+        const uint32_t col = w_col[t];
+        const int b = col & 15;
+        uint32_t pos = 0;
+#pragma unroll
+        for (int bb = 0; bb < 16; ++bb)
+            if (bb == b) pos = start[bb]++;
+        stage[pos * kGreedyThreads + threadIdx.x] = ((t - s) << 16) | col;
+    }
+    unsigned long long cnt[8];            // per group: 16 x 4-bit counters (saturating)
+    uint32_t tot[8], gmax[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { cnt[r] = 0; tot[r] = 0; gmax[r] = 0; }
+    const uint32_t n = e - s;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ent = stage[i * kGreedyThreads + threadIdx.x];
+        const uint32_t col = ent & 0xffffu, off = ent >> 16;
+        const int sh = 4 * (int)(col & 15);
+        uint32_t best = 0, best_key = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if ((uint32_t)r >= R || tot[r] >= 16) continue;
+            const uint32_t cb = (uint32_t)((cnt[r] >> sh) & 15ull);
+            const uint32_t key = ((uint32_t)(cb + 1 > gmax[r]) << 16) | (cb << 8) | tot[r];
+            if (key < best_key) { best_key = key; best = r; }
+        }
+        uint32_t slot = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if ((uint32_t)r == best) {
+                slot = tot[r]++;
+                const uint32_t cb = (uint32_t)((cnt[r] >> sh) & 15ull) + 1;
+                if (cb < 16) cnt[r] += 1ull << sh;
+                if (cb > gmax[r]) gmax[r] = cb;
+            }
+        }
+        const uint32_t dst = ps + best * 16 + slot;
+        p_col[dst] = (uint16_t)col;
+        if (p_val != nullptr) p_val[dst] = w_val[s + off];
     }
 }
 
@@ -320,7 +399,18 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, c->p_col.as<uint16_t>(),
                                                  binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
-    w_layout_kernel<<<(n_gene + 3) / 4, 128, 0, c->stream>>>(
+    w_layout_deal_kernel<<<(n_gene + 3) / 4, 128, 0, c->stream>>>(
+        n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(),
+        c->w_val.as<float>(), c->p_col.as<uint16_t>(), binary ? nullptr : c->p_val.as<float>());
+    SCDRS_LAUNCH_CHECK(c);
+    static bool greedy_attr = false;
+    if (!greedy_attr) {
+        SCDRS_CUDA(cudaFuncSetAttribute(w_layout_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kGreedyMaxLen * kGreedyThreads * (int)sizeof(uint32_t)));
+        greedy_attr = true;
+    }
+    w_layout_greedy_kernel<<<(n_gene + kGreedyThreads - 1) / kGreedyThreads, kGreedyThreads,
+                             kGreedyMaxLen * kGreedyThreads * sizeof(uint32_t), c->stream>>>(
         n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(),
         c->w_val.as<float>(), c->p_col.as<uint16_t>(), binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
@@ -422,28 +512,8 @@ __device__ __forceinline__ void acc_fma2(uint32_t acc_s, uint32_t q0, uint32_t q
         : "memory");
 }
 
-// the first 64 slots (four 16-slot groups) of one gene's list, as seen by one lane of the warp:
-// lanes 0-15 read groups 0 and 2, lanes 16-31 groups 1 and 3
-struct GeneSlots {
-    uint32_t c0, c1, t, ng;
-    float w0, w1;
-};
-
-template <bool WEIGHTED>
-__device__ __forceinline__ void fetch_slots(GeneSlots& s, uint32_t m, uint32_t lane,
-                                            const uint16_t* __restrict__ p_col,
-                                            const float* __restrict__ p_val) {
-    const uint32_t grp = lane >> 4;
-    s.t = ((m >> 12) << 4) + lane;
-    s.ng = m & 4095u;
-    s.c0 = grp < s.ng ? p_col[s.t] : 0xffffu;
-    s.c1 = grp + 2 < s.ng ? p_col[s.t + 32] : 0xffffu;
-    if (WEIGHTED) {
-        s.w0 = grp < s.ng ? p_val[s.t] : 0.f;
-        s.w1 = grp + 2 < s.ng ? p_val[s.t + 32] : 0.f;
-    }
-}
-
+// Lane l of the warp reads slots l and l + 32 of a gene's list: lanes 0-15 groups 0 and 2, lanes
+// 16-31 groups 1 and 3; longer lists (rare) are finished in a loop.
 // One warp per cell.  p_meta[g] = (first 16-slot group of gene g's list << 12) | number of groups.
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
@@ -475,38 +545,56 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
                 meta = (uint32_t)gi.z;
             }
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
-            // software pipeline, two entries deep: while entry i is applied, the set ids of entries
-            // i + 1 and i + 2 are in flight
-            GeneSlots sa, sb;
-            fetch_slots<WEIGHTED>(sa, __shfl_sync(0xffffffffu, meta, 0), lane, p_col, p_val);
-            fetch_slots<WEIGHTED>(sb, n > 1 ? __shfl_sync(0xffffffffu, meta, 1) : 0u, lane, p_col, p_val);
-            auto step = [&](GeneSlots& cur, int i) {
-                const uint32_t q0 = cur.c0, q1 = cur.c1, tc = cur.t, ngc = cur.ng;
-                const float v0 = cur.w0, v1 = cur.w1;
-                const double xi = __shfl_sync(0xffffffffu, xd, i);
-                uint32_t m = __shfl_sync(0xffffffffu, meta, (i + 2) & 31);
-                if (i + 2 >= n) m = 0;
-                fetch_slots<WEIGHTED>(cur, m, lane, p_col, p_val);
-                if (WEIGHTED)
-                    acc_fma2(acc_s, q0, q1, xi, v0, v1);
-                else
-                    acc_add2(acc_s, q0, q1, xi);
-                if (ngc > 4) {                                   // long lists (rare); warp-uniform
-#pragma unroll 1
-                    for (uint32_t gi = 4 + (lane >> 4); gi < ngc; gi += 2) {
-                        const uint32_t col = p_col[tc + (gi - (lane >> 4)) * 16];
-                        if (WEIGHTED)
-                            acc_fma(acc_s, col, xi, p_val[tc + (gi - (lane >> 4)) * 16]);
-                        else
-                            acc_add(acc_s, col, xi);
+            // software pipeline in blocks of four entries: the set ids of the next block are in
+            // flight (L2 latency, the lists rarely hit in L1) while the current block is applied
+            uint32_t a0[4], a1[4], b0[4], b1[4];
+            float aw0[4], aw1[4], bw0[4], bw1[4];
+            auto fetch4 = [&](uint32_t (&c0)[4], uint32_t (&c1)[4], float (&w0)[4], float (&w1)[4], int j) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t m = __shfl_sync(0xffffffffu, meta, (j + u) & 31);
+                    if (j + u >= n) m = 0;
+                    const uint32_t t = ((m >> 12) << 4) + lane, ng = m & 4095u, grp = lane >> 4;
+                    c0[u] = grp < ng ? p_col[t] : 0xffffu;
+                    c1[u] = grp + 2 < ng ? p_col[t + 32] : 0xffffu;
+                    if (WEIGHTED) {
+                        w0[u] = grp < ng ? p_val[t] : 0.f;
+                        w1[u] = grp + 2 < ng ? p_val[t + 32] : 0.f;
                     }
                 }
-                __syncwarp();
             };
+            auto apply4 = [&](uint32_t (&c0)[4], uint32_t (&c1)[4], float (&w0)[4], float (&w1)[4], int j) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j + u >= n) break;                       // warp-uniform
+                    const double xi = __shfl_sync(0xffffffffu, xd, j + u);
+                    const uint32_t m = __shfl_sync(0xffffffffu, meta, j + u);
+                    if (WEIGHTED)
+                        acc_fma2(acc_s, c0[u], c1[u], xi, w0[u], w1[u]);
+                    else
+                        acc_add2(acc_s, c0[u], c1[u], xi);
+                    const uint32_t ngc = m & 4095u;
+                    if (ngc > 4) {                               // long lists (rare); warp-uniform
+                        const uint32_t tc = ((m >> 12) << 4) + lane;
 #pragma unroll 1
-            for (int i = 0; i < n; i += 2) {
-                step(sa, i);
-                if (i + 1 < n) step(sb, i + 1);
+                        for (uint32_t gi = 4 + (lane >> 4); gi < ngc; gi += 2) {
+                            const uint32_t col = p_col[tc + (gi - (lane >> 4)) * 16];
+                            if (WEIGHTED)
+                                acc_fma(acc_s, col, xi, p_val[tc + (gi - (lane >> 4)) * 16]);
+                            else
+                                acc_add(acc_s, col, xi);
+                        }
+                    }
+                    __syncwarp();
+                }
+            };
+            fetch4(a0, a1, aw0, aw1, 0);
+#pragma unroll 1
+            for (int i = 0; i < n; i += 8) {
+                fetch4(b0, b1, bw0, bw1, i + 4);
+                apply4(a0, a1, aw0, aw1, i);
+                fetch4(a0, a1, aw0, aw1, i + 8);
+                apply4(b0, b1, bw0, bw1, i + 4);
             }
         }
         // epilogue: column scale, covariate terms, row reference, deviations

@@ -32,7 +32,7 @@ __device__ __forceinline__ double warp_sum_s(double v) {
 // kRowTile x kGeneTile dense tiles of X in shared memory (rows are located by binary search in the
 // sorted CSR column ids).  v = (x + sum_k C[c,k] B[g,k]) + mu with the k-sum accumulated in index
 // order by fma, as a BLAS dgemm micro-kernel does.  Bitwise reproducible.
-constexpr int kGeneTile = 128;
+constexpr int kGeneTile = 64;    // 313 tiles at 20k genes: ~2 resident CTAs per SM, no tail wave
 constexpr int kRowTile = 64;
 
 template <int TRANSFORM>
@@ -73,27 +73,38 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
             }
             __syncthreads();
             if (ok) {
-                for (int r = 0; r < nr; ++r) {
-                    double v = (double)tile[r][threadIdx.x];
-                    if (k > 0) {
-                        const double* crow = cov_mat + (r0 + r) * k;
-                        double cb = crow[0] * sdyn[threadIdx.x];
-                        for (int kk = 1; kk < k; ++kk) cb = fma(crow[kk], sdyn[kk * kGeneTile + threadIdx.x], cb);
-                        v = (v + cb) + mu;
-                    }
-                    const double t = apply_t<TRANSFORM>(v);
-                    const double w = cell_w != nullptr ? cell_w[r0 + r] : 1.0;
-                    // explicit _rn intrinsics: no fma contraction, numpy multiplies then adds
-                    if (pass == 0) {
-                        s = __dadd_rn(s, cell_w != nullptr ? __dmul_rn(t, w) : t);
-                        if (!center) {
-                            const double t2 = __dmul_rn(t, t);
-                            q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(t2, w) : t2);
+                // four cells at a time: the transforms are independent (instruction-level parallelism),
+                // the accumulation stays strictly in cell order
+                for (int rb = 0; rb < nr; rb += 4) {
+                    double t[4], w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + u < nr ? rb + u : nr - 1;
+                        double v = (double)tile[r][threadIdx.x];
+                        if (k > 0) {
+                            const double* crow = cov_mat + (r0 + r) * k;
+                            double cb = crow[0] * sdyn[threadIdx.x];
+                            for (int kk = 1; kk < k; ++kk) cb = fma(crow[kk], sdyn[kk * kGeneTile + threadIdx.x], cb);
+                            v = (v + cb) + mu;
                         }
-                    } else {
-                        const double d = __dadd_rn(t, -mean);
-                        const double d2 = __dmul_rn(d, d);
-                        q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(d2, w) : d2);
+                        t[u] = apply_t<TRANSFORM>(v);
+                        w[u] = cell_w != nullptr ? cell_w[r0 + r] : 1.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (rb + u >= nr) break;
+                        // explicit _rn intrinsics: no fma contraction, numpy multiplies then adds
+                        if (pass == 0) {
+                            s = __dadd_rn(s, cell_w != nullptr ? __dmul_rn(t[u], w[u]) : t[u]);
+                            if (!center) {
+                                const double t2 = __dmul_rn(t[u], t[u]);
+                                q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(t2, w[u]) : t2);
+                            }
+                        } else {
+                            const double d = __dadd_rn(t[u], -mean);
+                            const double d2 = __dmul_rn(d, d);
+                            q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(d2, w[u]) : d2);
+                        }
                     }
                 }
             }
