@@ -128,25 +128,34 @@ __global__ void w_count_kernel(int64_t n_entry, const int32_t* __restrict__ set_
 __global__ void w_padded_len_kernel(int n_gene, const uint32_t* __restrict__ cnt,
                                     uint32_t* __restrict__ plen) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_gene) plen[g] = (cnt[g] + 15u) & ~15u;
+    if (g < n_gene) plen[g] = (cnt[g] + 63u) & ~63u;
     if (g == n_gene) plen[g] = 0;
+}
+
+// Storage index of slot q of a gene's list (group q/16, position q%16).  Lists are stored in blocks of
+// 64 slots; inside a block the slots that one lane of the scatter kernel consumes together (slot l of
+// groups 0/1 and slot l of groups 2/3) are adjacent, so that the lane fetches both set ids with one
+// 32-bit load (and both weights with one 64-bit load).
+__host__ __device__ __forceinline__ uint32_t slot_index(uint32_t q) {
+    const uint32_t grp = q >> 4, pos = q & 15u;
+    return (((grp >> 2) * 32u + (grp & 1u) * 16u + pos) << 1) | ((grp >> 1) & 1u);
 }
 
 // per gene, fetched with ONE 16-byte load per stored entry of X: the base weight folded into the
 // expression value and the packed location of the gene's set-id list
 struct __align__(16) GeneInfo {
     double base;
-    uint32_t meta;   // (first 16-slot group << 12) | number of groups
+    uint32_t meta;   // (first 64-slot block << 12) | number of 16-slot groups
     uint32_t pad;
 };
 
-__global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, const double* __restrict__ gbase,
-                              GeneInfo* __restrict__ info) {
+__global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
+                              const double* __restrict__ gbase, GeneInfo* __restrict__ info) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n_gene) {
         GeneInfo gi;
         gi.base = gbase[g];
-        gi.meta = ((p_ptr[g] >> 4) << 12) | ((p_ptr[g + 1] - p_ptr[g]) >> 4);
+        gi.meta = ((p_ptr[g] >> 6) << 12) | ((w_ptr[g + 1] - w_ptr[g] + 15u) >> 4);
         gi.pad = 0;
         info[g] = gi;
     }
@@ -187,7 +196,7 @@ w_layout_deal_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint3
     const int g = blockIdx.x * 4 + warp;
     if (g >= n_gene) return;
     const uint32_t s = w_ptr[g], e = w_ptr[g + 1];
-    const uint32_t ps = p_ptr[g], R = (p_ptr[g + 1] - ps) >> 4;
+    const uint32_t ps = p_ptr[g], R = (e - s + 15u) >> 4;
     if (e == s || R <= 8) return;   // short lists are placed by w_layout_greedy_kernel
     if (lane < 16) { hist[warp][lane] = 0; run[warp][lane] = 0; }
     __syncwarp();
@@ -222,7 +231,7 @@ w_layout_deal_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint3
         if (ok && rank == 0) run[warp][pair] += __popc(peers);
         __syncwarp();
         if (ok) {
-            const uint32_t dst = ps + (i % R) * 16 + (i / R);
+            const uint32_t dst = ps + slot_index((i % R) * 16 + (i / R));
             p_col[dst] = (uint16_t)col;
             if (p_val != nullptr) p_val[dst] = v;
         }
@@ -246,7 +255,7 @@ w_layout_greedy_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uin
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_gene) return;
     const uint32_t s = w_ptr[g], e = w_ptr[g + 1];
-    const uint32_t ps = p_ptr[g], R = (p_ptr[g + 1] - ps) >> 4;
+    const uint32_t ps = p_ptr[g], R = (e - s + 15u) >> 4;
     if (e == s || R > 8) return;
     uint32_t c[16];
 #pragma unroll
@@ -302,7 +311,7 @@ w_layout_greedy_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uin
                 if (cb > gmax[r]) gmax[r] = cb;
             }
         }
-        const uint32_t dst = ps + best * 16 + slot;
+        const uint32_t dst = ps + slot_index(best * 16 + slot);
         p_col[dst] = (uint16_t)col;
         if (p_val != nullptr) p_val[dst] = w_val[s + off];
     }
@@ -350,12 +359,12 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_TRY(c->w_cursor.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_meta.reserve((size_t)(n_gene + 1) * sizeof(GeneInfo)));
-    SCDRS_CHECK(n_entry + 16 * (int64_t)n_gene < ((int64_t)1 << 24), "gene-set lists too large for the packed index");
+    SCDRS_CHECK(n_entry + 64 * (int64_t)n_gene < ((int64_t)1 << 26), "gene-set lists too large for the packed index");
     SCDRS_CHECK(ncol <= 4095 * 16, "too many gene sets");
     SCDRS_TRY(c->w_col.reserve(n_entry * sizeof(uint16_t)));
     SCDRS_TRY(c->w_val.reserve(n_entry * sizeof(float)));
     // padded size: every non-empty gene rounds up to a multiple of 32 slots
-    const int64_t n_slot_max = n_entry + 15 * (int64_t)(n_gene < n_entry ? n_gene : n_entry);
+    const int64_t n_slot_max = n_entry + 63 * (int64_t)(n_gene < n_entry ? n_gene : n_entry) + 64;
     SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
     if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
     c->w_binary = binary;
@@ -387,7 +396,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                                                      c->p_ptr.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     SCDRS_TRY(exclusive_scan_u32(c, c->p_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), n_gene + 1));
-    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
+    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
                                                                c->p_meta.as<GeneInfo>());
     SCDRS_LAUNCH_CHECK(c);
     SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
@@ -486,7 +495,8 @@ __device__ __forceinline__ void acc_fma(uint32_t acc_s, uint32_t col, double x, 
 
 // Two independent read-modify-writes (the set ids of one gene are distinct, so the addresses
 // differ): loads first, then adds, then stores, to overlap the shared-memory latencies.
-__device__ __forceinline__ void acc_add2(uint32_t acc_s, uint32_t q0, uint32_t q1, double x) {
+__device__ __forceinline__ void acc_add2(uint32_t acc_s, uint32_t both, double x) {
+    const uint32_t q0 = both & 0xffffu, q1 = both >> 16;
     asm volatile(
         "{\n\t.reg .pred p0, p1;\n\t.reg .f64 v0, v1;\n\t.reg .u32 a0, a1;\n\t"
         "setp.ne.u32 p0, %1, 0xffff;\n\tsetp.ne.u32 p1, %2, 0xffff;\n\t"
@@ -498,7 +508,8 @@ __device__ __forceinline__ void acc_add2(uint32_t acc_s, uint32_t q0, uint32_t q
         ::"r"(acc_s), "r"(q0), "r"(q1), "d"(x)
         : "memory");
 }
-__device__ __forceinline__ void acc_fma2(uint32_t acc_s, uint32_t q0, uint32_t q1, double x, float w0, float w1) {
+__device__ __forceinline__ void acc_fma2(uint32_t acc_s, uint32_t both, double x, float w0, float w1) {
+    const uint32_t q0 = both & 0xffffu, q1 = both >> 16;
     asm volatile(
         "{\n\t.reg .pred p0, p1;\n\t.reg .f64 v0, v1, d0, d1;\n\t.reg .u32 a0, a1;\n\t"
         "setp.ne.u32 p0, %1, 0xffff;\n\tsetp.ne.u32 p1, %2, 0xffff;\n\t"
@@ -512,11 +523,11 @@ __device__ __forceinline__ void acc_fma2(uint32_t acc_s, uint32_t q0, uint32_t q
         : "memory");
 }
 
-// Lane l of the warp reads slots l and l + 32 of a gene's list: lanes 0-15 groups 0 and 2, lanes
-// 16-31 groups 1 and 3; longer lists (rare) are finished in a loop.
+// Lane l of the warp consumes slots l and l + 32 of every 64-slot block of a gene's list: lanes 0-15
+// groups 0 and 2, lanes 16-31 groups 1 and 3; lists longer than one block (rare) continue in a loop.
 // One warp per cell.  p_meta[g] = (first 16-slot group of gene g's list << 12) | number of groups.
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                   const float* __restrict__ data, const GeneInfo* __restrict__ ginfo,
@@ -529,6 +540,8 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* acc = reinterpret_cast<double*>(smem_raw) + (size_t)warp * acc_stride;
     const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    const uint32_t* __restrict__ p_col32 = reinterpret_cast<const uint32_t*>(p_col);
+    const float2* __restrict__ p_val2 = reinterpret_cast<const float2*>(p_val);
 
     for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell;
          row += (int64_t)gridDim.x * wpb) {
@@ -547,54 +560,63 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
             const int n = (int)((p1 - base) < 32 ? (p1 - base) : 32);
             // software pipeline in blocks of four entries: the set ids of the next block are in
             // flight (L2 latency, the lists rarely hit in L1) while the current block is applied
-            uint32_t a0[4], a1[4], b0[4], b1[4];
+            uint32_t a_ids[4], a_m[4], b_ids[4], b_m[4];      // packed set ids of groups (0|1),(2|3); meta
             float aw0[4], aw1[4], bw0[4], bw1[4];
-            auto fetch4 = [&](uint32_t (&c0)[4], uint32_t (&c1)[4], float (&w0)[4], float (&w1)[4], int j) {
+            auto fetch4 = [&](uint32_t (&ids)[4], uint32_t (&mm)[4], float (&w0)[4], float (&w1)[4], int j) {
+                if (j >= n) {                                    // warp-uniform: nothing left in this chunk
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { ids[u] = 0xffffffffu; mm[u] = 0; }
+                    return;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     uint32_t m = __shfl_sync(0xffffffffu, meta, (j + u) & 31);
                     if (j + u >= n) m = 0;
-                    const uint32_t t = ((m >> 12) << 4) + lane, ng = m & 4095u, grp = lane >> 4;
-                    c0[u] = grp < ng ? p_col[t] : 0xffffu;
-                    c1[u] = grp + 2 < ng ? p_col[t + 32] : 0xffffu;
+                    // one 32-bit load brings this lane's set ids of groups (0|1) and (2|3); slots past
+                    // the end of the list hold 0xffff
+                    const uint32_t t = (m >> 12) * 32u + lane;
+                    ids[u] = (m & 4095u) ? __ldg(p_col32 + t) : 0xffffffffu;
+                    mm[u] = m;
                     if (WEIGHTED) {
-                        w0[u] = grp < ng ? p_val[t] : 0.f;
-                        w1[u] = grp + 2 < ng ? p_val[t + 32] : 0.f;
+                        const float2 w = (m & 4095u) ? __ldg(p_val2 + t) : make_float2(0.f, 0.f);
+                        w0[u] = w.x;
+                        w1[u] = w.y;
                     }
                 }
             };
-            auto apply4 = [&](uint32_t (&c0)[4], uint32_t (&c1)[4], float (&w0)[4], float (&w1)[4], int j) {
+            auto apply4 = [&](uint32_t (&ids)[4], uint32_t (&mm)[4], float (&w0)[4], float (&w1)[4], int j) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (j + u >= n) break;                       // warp-uniform
                     const double xi = __shfl_sync(0xffffffffu, xd, j + u);
-                    const uint32_t m = __shfl_sync(0xffffffffu, meta, j + u);
                     if (WEIGHTED)
-                        acc_fma2(acc_s, c0[u], c1[u], xi, w0[u], w1[u]);
+                        acc_fma2(acc_s, ids[u], xi, w0[u], w1[u]);
                     else
-                        acc_add2(acc_s, c0[u], c1[u], xi);
-                    const uint32_t ngc = m & 4095u;
+                        acc_add2(acc_s, ids[u], xi);
+                    const uint32_t m = mm[u], ngc = m & 4095u;
                     if (ngc > 4) {                               // long lists (rare); warp-uniform
-                        const uint32_t tc = ((m >> 12) << 4) + lane;
+                        const uint32_t t0 = (m >> 12) * 32u + lane;
 #pragma unroll 1
-                        for (uint32_t gi = 4 + (lane >> 4); gi < ngc; gi += 2) {
-                            const uint32_t col = p_col[tc + (gi - (lane >> 4)) * 16];
-                            if (WEIGHTED)
-                                acc_fma(acc_s, col, xi, p_val[tc + (gi - (lane >> 4)) * 16]);
-                            else
-                                acc_add(acc_s, col, xi);
+                        for (uint32_t blk = 1; blk * 4 < ngc; ++blk) {
+                            const uint32_t both = __ldg(p_col32 + t0 + blk * 32u);
+                            if (WEIGHTED) {
+                                const float2 w = __ldg(p_val2 + t0 + blk * 32u);
+                                acc_fma2(acc_s, both, xi, w.x, w.y);
+                            } else {
+                                acc_add2(acc_s, both, xi);
+                            }
                         }
                     }
                     __syncwarp();
                 }
             };
-            fetch4(a0, a1, aw0, aw1, 0);
+            fetch4(a_ids, a_m, aw0, aw1, 0);
 #pragma unroll 1
             for (int i = 0; i < n; i += 8) {
-                fetch4(b0, b1, bw0, bw1, i + 4);
-                apply4(a0, a1, aw0, aw1, i);
-                fetch4(a0, a1, aw0, aw1, i + 8);
-                apply4(b0, b1, bw0, bw1, i + 4);
+                fetch4(b_ids, b_m, bw0, bw1, i + 4);
+                apply4(a_ids, a_m, aw0, aw1, i);
+                fetch4(a_ids, a_m, aw0, aw1, i + 8);
+                apply4(b_ids, b_m, bw0, bw1, i + 4);
             }
         }
         // epilogue: column scale, covariate terms, row reference, deviations
