@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--n-ctrl", type=int, default=1000)
     ap.add_argument("--density", type=float, default=0.10)
     ap.add_argument("--weighted", action="store_true", help="MAGMA-z-like gene weights (BASELINE configs[2])")
+    ap.add_argument("--spmm", default="auto", choices=["auto", "f64", "fixed"],
+                    help="arithmetic of the raw-score scatter (auto: exact fixed point when it applies)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=30000)
@@ -319,6 +321,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     scdrs_b200.set_default_device(local_rank)
+    scdrs_b200.set_spmm_mode(args.spmm)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -404,7 +407,11 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")
     if os.path.exists(tpath) and (args.n_cell, args.n_gene, args.n_ctrl) == (110096, 20000, 1000):
         traffic = float(json.load(open(tpath))["dram_bytes_total"])   # from the committed ncu capture
-    roofline = {"bound": "hbm", "kernel": "spmm_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    spmm_kind, spmm_shift = ctx.last_spmm_kind()
+    roofline = {"bound": "hbm", "kernel": "spmm_score_fx_kernel" if spmm_kind == "fixed" else "spmm_score_kernel",
+                "arithmetic": ("exact integer sums of round(x*base*2^%d), 32-bit shared-memory words, 64-bit totals" % spmm_shift)
+                if spmm_kind == "fixed" else "fp64 accumulators in shared memory",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_ms,
                 "scatter_fma_per_launch": float(nnz) * (1 + n_ctrl) * args.n_trait_gene / args.n_gene,

@@ -1,6 +1,7 @@
 """Per-AnnData device residency: the expression matrix is uploaded once and reused by every
 ``score_cell`` / ``compute_stats`` call on the same object (the reference re-slices a CSC copy on
 every call, scdrs/method.py:98-99, :389-400)."""
+import os
 import weakref
 
 import numpy as np
@@ -10,11 +11,22 @@ from . import _native
 
 _STATES = {}  # id(adata) -> DeviceState
 _DEFAULT_DEVICE = [0]
+_SPMM_MODE = [os.environ.get("SCDRS_B200_SPMM", "auto")]
 
 
 def set_default_device(device):
     """GPU index new device states are created on (one process per GPU under torchrun)."""
     _DEFAULT_DEVICE[0] = int(device)
+
+
+def set_spmm_mode(mode):
+    """Arithmetic of the raw-score scatter: "auto" (exact fixed-point sums when they apply, else
+    fp64 accumulators), "f64" or "fixed" (raise when not applicable).  Applies to live and future
+    device states; the environment variable SCDRS_B200_SPMM sets the initial value."""
+    assert mode in ("auto", "f64", "fixed"), mode
+    _SPMM_MODE[0] = mode
+    for st in _STATES.values():
+        st.ctx.set_spmm_mode(mode)
 
 
 def clear_device_cache():
@@ -49,6 +61,7 @@ def to_csr_parts(X):
 class DeviceState:
     def __init__(self, adata, device):
         self.ctx = _native.Context(device)
+        self.ctx.set_spmm_mode(_SPMM_MODE[0])
         self.x_fp = None
         self.cov_fp = None
         self.h2d_bytes = 0

@@ -29,6 +29,8 @@ SIGNATURES = {
     "scdrs_ctx_sync": (C.c_int, [C.c_void_p]),
     "scdrs_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "scdrs_ctx_last_timing": (C.c_int, [C.c_void_p, c_f32p, c_f32p]),
+    "scdrs_ctx_set_spmm_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "scdrs_ctx_last_spmm_kind": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scdrs_set_csr_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_set_csr_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_set_gene_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -157,6 +159,15 @@ class Context:
 
     def launch_count(self):
         return int(self._L.scdrs_ctx_launch_count(self._h))
+
+    def set_spmm_mode(self, mode):
+        """0 auto, 1 fp64 accumulators, 2 fixed point (raises when it does not apply)."""
+        check(self._L.scdrs_ctx_set_spmm_mode(self._h, {"auto": 0, "f64": 1, "fixed": 2}.get(mode, mode)))
+
+    def last_spmm_kind(self):
+        a, b = C.c_int32(), C.c_int32()
+        check(self._L.scdrs_ctx_last_spmm_kind(self._h, C.byref(a), C.byref(b)))
+        return ("fixed" if a.value else "f64"), b.value
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()

@@ -67,7 +67,8 @@ static void release_all(scdrs_ctx* c) {
                       &c->row_mean, &c->row_istd, &c->scalars, &c->query, &c->mc_count, &c->norm_mat,
                       &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
-                      &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage};
+                      &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
+                      &c->w_code, &c->w_rounds, &c->fx_part};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -171,6 +172,21 @@ int scdrs_ctx_sync(scdrs_ctx* c) {
 
 int64_t scdrs_ctx_launch_count(scdrs_ctx* c) { return c ? c->launches : -1; }
 
+int scdrs_ctx_set_spmm_mode(scdrs_ctx* c, int32_t mode) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(mode >= 0 && mode <= 2, "spmm mode %d outside [0, 2]", mode);
+    c->spmm_mode = mode;
+    c->trait_ready = false;
+    return 0;
+}
+
+int scdrs_ctx_last_spmm_kind(scdrs_ctx* c, int32_t* fixed_point, int32_t* scale_log2) {
+    CTX_GUARD(c);
+    if (fixed_point) *fixed_point = c->w_fx ? 1 : 0;
+    if (scale_log2) *scale_log2 = c->w_fx ? c->fx_shift : 0;
+    return 0;
+}
+
 int scdrs_ctx_last_timing(scdrs_ctx* c, float* spmm_ms, float* trait_ms) {
     CTX_GUARD(c);
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
@@ -210,6 +226,7 @@ int scdrs_set_csr_host(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64
     c->nnz = nnz;
     c->trait_ready = false;
     c->have_stats = false;
+    c->fx_stat_key = -1;
     c->k = 0;
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -231,6 +248,7 @@ int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_
     c->nnz = nnz;
     c->trait_ready = false;
     c->have_stats = false;
+    c->fx_stat_key = -1;
     c->k = 0;
     return 0;
 }
@@ -243,6 +261,7 @@ int scdrs_set_gene_stats(scdrs_ctx* c, const double* var, const double* var_tech
     SCDRS_TRY(h2d(c, c->var_tech, var_tech, (size_t)c->n_gene * sizeof(double)));
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     c->have_stats = true;
+    c->fx_stat_key = -1;
     return 0;
 }
 

@@ -77,6 +77,14 @@ struct scdrs_ctx {
     scdrs::DevBuf w_ptr, w_cursor, w_col, w_val;        // compact gene-major lists (build scratch)
     scdrs::DevBuf p_ptr, p_meta, p_col, p_val, colscale, gbase;  // padded / bank-dealt lists the scatter reads
     bool w_binary = false;
+    // fixed-point scatter (spmm_score_fx.cu)
+    int spmm_mode = 0;        // 0 auto, 1 fp64 accumulators, 2 fixed point (error if not applicable)
+    bool w_fx = false;        // the lists currently built are laid out for the fixed-point kernel
+    int fx_shift = 0;         // scale = 2^fx_shift
+    int fx_stat_key = -1;     // weight_opt the value statistics below were computed for (-1: none)
+    double fx_vmax = 0.0, fx_vmean = 0.0;   // max and mean of |x * base_g| over the stored entries
+    float fx_gwmax = 1.f;
+    scdrs::DevBuf w_code, w_rounds, fx_part;
     scdrs::DevBuf dev_mat;   // float [n_cell x ld]: raw score minus the row reference; NaN = exact 0
     scdrs::DevBuf row_ref;   // double [n_cell]
     scdrs::DevBuf partial;   // double scratch for per-CTA column partials
@@ -104,6 +112,21 @@ int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
 int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
                      const double* w);
 int spmm_score(scdrs_ctx* c);
+
+// per gene, fetched with ONE 16-byte load per stored entry of X: the base weight folded into the
+// expression value and the packed location of the gene's set-id list
+struct __align__(16) GeneInfo {
+    double base;
+    uint32_t meta;
+    uint32_t pad;
+};
+
+// ---- spmm_score_fx.cu ---------------------------------------------------------------------
+constexpr int kFxMaxCol = 1024;   // the fixed-point kernel keeps one 64-bit total per column and lane in registers
+bool fx_applicable(scdrs_ctx* c, int ncol, bool explicit_w);
+int fx_value_stats(scdrs_ctx* c, int weight_opt);
+int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax);
+int fx_spmm(scdrs_ctx* c);
 
 // ---- background.cu ------------------------------------------------------------------------
 int bg_colsum(scdrs_ctx* c, double* dev_colsum_out);

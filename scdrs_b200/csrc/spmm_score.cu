@@ -20,6 +20,8 @@
 // Accumulation is fp64 like the reference's (float32 data times float64 weights,
 // scdrs/method.py:392-400).  The result is written as an fp64 per-cell reference value plus fp32
 // deviations from it, NaN marking exact zeros (the `raw == 0` rule, scdrs/method.py:522-523).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace scdrs {
@@ -141,13 +143,7 @@ __host__ __device__ __forceinline__ uint32_t slot_index(uint32_t q) {
     return (((grp >> 2) * 32u + (grp & 1u) * 16u + pos) << 1) | ((grp >> 1) & 1u);
 }
 
-// per gene, fetched with ONE 16-byte load per stored entry of X: the base weight folded into the
-// expression value and the packed location of the gene's set-id list
-struct __align__(16) GeneInfo {
-    double base;
-    uint32_t meta;   // (first 64-slot block << 12) | number of 16-slot groups
-    uint32_t pad;
-};
+// GeneInfo (common.cuh): meta = (first 64-slot block << 12) | number of 16-slot groups
 
 __global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* __restrict__ p_ptr,
                               const double* __restrict__ gbase, GeneInfo* __restrict__ info) {
@@ -346,7 +342,8 @@ static int upload_sets(scdrs_ctx* c, const int32_t* trait_genes, const int32_t* 
     return 0;
 }
 
-static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explicit_w, bool binary) {
+static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explicit_w, bool binary,
+                   double gw_absmax) {
     const int ncol = c->ncol, n_s = c->n_s, n_sc = c->n_sc, n_gene = c->n_gene;
     const int64_t n_entry = (int64_t)n_s + (int64_t)c->n_ctrl * n_sc;
     SCDRS_TRY(c->covM.reserve((size_t)(c->k > 0 ? c->k : 1) * ncol * sizeof(double)));
@@ -363,11 +360,8 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_CHECK(ncol <= 4095 * 16, "too many gene sets");
     SCDRS_TRY(c->w_col.reserve(n_entry * sizeof(uint16_t)));
     SCDRS_TRY(c->w_val.reserve(n_entry * sizeof(float)));
-    // padded size: every non-empty gene rounds up to a multiple of 32 slots
-    const int64_t n_slot_max = n_entry + 63 * (int64_t)(n_gene < n_entry ? n_gene : n_entry) + 64;
-    SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
-    if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
     c->w_binary = binary;
+    c->w_fx = false;
 
     gene_base_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(
         n_gene, explicit_w ? SCDRS_WEIGHT_UNIFORM : weight_opt,
@@ -386,6 +380,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                                             c->ratio_a.as<double>());
     SCDRS_LAUNCH_CHECK(c);
 
+    // compact gene-major lists: for gene g the ids (and .gs weights) of the sets that contain it
     SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
     const int nb = (int)((n_entry + 255) / 256 < 1184 ? (n_entry + 255) / 256 : 1184);
     w_count_kernel<<<nb, 256, 0, c->stream>>>(n_entry, c->set_genes.as<int32_t>(),
@@ -395,15 +390,32 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     w_padded_len_kernel<<<(n_gene + 256) / 256, 256, 0, c->stream>>>(n_gene, c->w_cursor.as<uint32_t>(),
                                                                      c->p_ptr.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
-    SCDRS_TRY(exclusive_scan_u32(c, c->p_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), n_gene + 1));
-    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
-                                                               c->p_meta.as<GeneInfo>());
-    SCDRS_LAUNCH_CHECK(c);
     SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
     w_fill_kernel<<<nb, 256, 0, c->stream>>>(n_entry, n_s, n_sc > 0 ? n_sc : 1, c->set_genes.as<int32_t>(),
                                              c->set_w.as<float>(), c->w_ptr.as<uint32_t>(),
                                              c->w_cursor.as<uint32_t>(), c->w_col.as<uint16_t>(),
                                              c->w_val.as<float>());
+    SCDRS_LAUNCH_CHECK(c);
+
+    // fixed-point scatter when it applies (spmm_score_fx.cu), else fp64 accumulators
+    bool use_fx = fx_applicable(c, ncol, explicit_w);
+    if (use_fx) {
+        SCDRS_TRY(fx_value_stats(c, weight_opt));
+        use_fx = c->fx_vmax > 0.0 && c->fx_vmax <= 128.0 * c->fx_vmean && gw_absmax > 0.0 &&
+                 gw_absmax < 1e30;
+    }
+    SCDRS_CHECK(use_fx || c->spmm_mode != 2,
+                "fixed-point scatter requested but not applicable (needs 1 + n_ctrl <= %d, a trait prepared by "
+                "scdrs_trait_raw and max|x*base| <= 128 mean|x*base|)", kFxMaxCol);
+    if (use_fx) return fx_layout(c, binary, binary ? 1.0 : gw_absmax);
+
+    // padded size: every non-empty gene rounds up to a multiple of 64 slots
+    const int64_t n_slot_max = n_entry + 63 * (int64_t)(n_gene < n_entry ? n_gene : n_entry) + 64;
+    SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
+    if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
+    SCDRS_TRY(exclusive_scan_u32(c, c->p_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), n_gene + 1));
+    w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
+                                                               c->p_meta.as<GeneInfo>());
     SCDRS_LAUNCH_CHECK(c);
     w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, c->p_col.as<uint16_t>(),
                                                  binary ? nullptr : c->p_val.as<float>());
@@ -454,15 +466,18 @@ int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
     bool binary = true;
     for (int i = 1; i < n_s && binary; ++i) binary = trait_gw[i] == trait_gw[0];
     for (int i = 0; i < n_s_ctrl && binary && n_ctrl > 0; ++i) binary = ctrl_gw[i] == trait_gw[0];
+    double gw_absmax = 0.0;
+    for (int i = 0; i < n_s; ++i) gw_absmax = fabs(trait_gw[i]) > gw_absmax ? fabs(trait_gw[i]) : gw_absmax;
+    for (int i = 0; i < n_s_ctrl && n_ctrl > 0; ++i) gw_absmax = fabs(ctrl_gw[i]) > gw_absmax ? fabs(ctrl_gw[i]) : gw_absmax;
     SCDRS_TRY(upload_sets(c, trait_genes, ctrl_genes, trait_gw, ctrl_gw, nullptr));
-    return build_w(c, weight_opt, use_var_ratio, false, binary);
+    return build_w(c, weight_opt, use_var_ratio, false, binary, gw_absmax);
 }
 
 int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
                      const double* w) {
     SCDRS_TRY(set_shape(c, n_set, n_s, n_s));
     SCDRS_TRY(upload_sets(c, nullptr, genes, nullptr, nullptr, w));
-    return build_w(c, SCDRS_WEIGHT_UNIFORM, 0, true, false);
+    return build_w(c, SCDRS_WEIGHT_UNIFORM, 0, true, false, 1.0);
 }
 
 // ---- the scatter kernel ----------------------------------------------------------------------
@@ -645,6 +660,7 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
 }
 
 int spmm_score(scdrs_ctx* c) {
+    if (c->w_fx) return fx_spmm(c);
     const int ncol = c->ncol;
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));

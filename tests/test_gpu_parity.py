@@ -15,11 +15,16 @@ RTOL = 1e-5     # north_star: raw, normalised and z-scores within 1e-5 relative 
 ATOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def sc(native_lib):
+@pytest.fixture(scope="module", params=["auto", "f64"])
+def sc(native_lib, request):
+    """The package with the raw-score scatter in its default arithmetic (fixed point where it
+    applies) and forced to fp64 accumulators: every parity test runs against both kernels."""
     import scdrs_b200
+    from scdrs_b200 import _device
 
-    return scdrs_b200
+    _device.set_spmm_mode(request.param)
+    yield scdrs_b200
+    _device.set_spmm_mode("auto")
 
 
 @pytest.fixture(scope="module")
@@ -491,3 +496,79 @@ def test_preprocess_param_schema_four_modes(sc):
         sc.preprocess(adata, cov=cov.set_index(pd.Index(["x%d" % i for i in range(300)])))
     with pytest.raises(AssertionError, match="adj_prop"):
         sc.preprocess(adata, adj_prop="nope")
+
+
+# ---- the two arithmetics of the raw-score scatter (spmm_score.cu / spmm_score_fx.cu) ---------------
+def _score_in_mode(mode, adata, genes, w, **kw):
+    import scdrs_b200
+    from scdrs_b200 import _device
+
+    _device.set_spmm_mode(mode)
+    try:
+        df = scdrs_b200.score_cell(adata, genes, gene_weight=w, **kw)
+        kind = _device._STATES[id(adata)].ctx.last_spmm_kind()
+    finally:
+        _device.set_spmm_mode("auto")
+    return df, kind
+
+
+@pytest.mark.parametrize("n_gene,n_trait_gene,weighted", [
+    (4000, 300, False),    # ~75 sets per gene: lists of two and three blocks
+    (4000, 300, True),
+    (400, 120, False),     # ~300 sets per gene: lists beyond the matching's 128 entries (greedy placement)
+    (400, 120, True),
+])
+def test_fixed_point_scatter_against_fp64_and_oracle(native_lib, n_gene, n_trait_gene, weighted):
+    """n_ctrl = 1000: the fixed-point kernel (integer sums, two accumulator words per set) against the
+    fp64 kernel and the oracle; it must also be bitwise reproducible although the gene-major lists are
+    built with atomics (integer sums do not depend on the order)."""
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    n_cell, n_ctrl = 600, 1000
+    adata, cov = synth.make_adata(n_cell, n_gene, density=0.1, seed=5)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    genes, w = synth.make_traits(adata.var_names, 1, n_trait_gene, weighted=weighted, seed=9)["trait_00"]
+    kw = dict(n_ctrl=n_ctrl, return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+    fx, kind = _score_in_mode("fixed", adata, genes, w, **kw)
+    assert kind[0] == "fixed" and kind[1] > 0
+    fx2, _ = _score_in_mode("fixed", adata, genes, w, **kw)
+    assert np.array_equal(fx.values, fx2.values)
+    f64, kind64 = _score_in_mode("f64", adata, genes, w, **kw)
+    assert kind64[0] == "f64"
+    cr = ["ctrl_raw_score_%d" % i for i in range(n_ctrl)]
+    cn = ["ctrl_norm_score_%d" % i for i in range(n_ctrl)]
+    # quantisation: 2^-26 of the largest entry per item (an absolute error: a raw score made of one
+    # small entry sees it relative to the largest) -> far inside the 1e-5 tolerance
+    top = float(np.abs(f64[cr].values).max())
+    assert np.allclose(fx[cr].values, f64[cr].values, rtol=1e-6, atol=2e-7 * top)
+    assert np.allclose(fx["raw_score"].values, f64["raw_score"].values, rtol=1e-6, atol=2e-7 * top)
+    assert np.abs(fx[cn].values - f64[cn].values).max() < 2e-5
+    ref = orc.score_cell(adata, genes, gene_weight=w, **kw)
+    _check_counts_self_consistent(fx, n_ctrl)
+    _compare_with_reference(fx, ref, n_ctrl, n_cell)
+
+
+def test_fixed_point_scatter_falls_back_on_outliers_and_wide_matrices(native_lib):
+    """One stored value 1e5 times the others would cost the fixed-point scale 17 bits: auto mode runs
+    the fp64 kernel (and "fixed" refuses); so does 1 + n_ctrl > 1024."""
+    from scdrs_b200 import _device, synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(300, 1500, density=0.1, seed=6)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    genes, w = synth.make_traits(adata.var_names, 1, 100, weighted=False, seed=10)["trait_00"]
+    df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=1100)
+    assert kind[0] == "f64"
+    with pytest.raises(RuntimeError, match="fixed-point scatter requested"):
+        _score_in_mode("fixed", adata, genes, w, n_ctrl=1100)
+    df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=50)
+    assert kind[0] == "fixed"
+    X = adata.X.copy()
+    X.data[7] *= 1e5
+    adata.X = X
+    _device.clear_device_cache()
+    ref = orc.score_cell(adata, genes, gene_weight=w, n_ctrl=50)
+    df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=50)
+    assert kind[0] == "f64"
+    _compare_with_reference(df, ref, 50, 300)
