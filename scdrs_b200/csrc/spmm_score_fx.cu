@@ -32,6 +32,7 @@ constexpr int kFxTrashOff = 2 * kFxNB * 4;    // byte offset of the 32 per-lane 
 constexpr int kFxItemOff = kFxTrashOff + 128;   // byte offset of the staged work items (list block, value)
 constexpr int kFxItemCap = 128;                 // four passes over a chunk of 32 stored entries
 constexpr int kFxMaxDepth = 8;                  // register slots of the item pipeline
+constexpr int kFxWarpsPerBlock = 10, kFxBlocksPerSM = 2;   // 20 warps per SM at <= 96 registers
 constexpr int kFxWarpBytes = kFxItemOff + (kFxItemCap + kFxMaxDepth) * 8;
 constexpr int kFxItemBits = 25;               // |item| <= 2^25: 32 stored entries add at most 2^30
 constexpr uint32_t kFxFlushAt = 0x7f000000u;  // flush before the bound on any word reaches this
@@ -88,7 +89,8 @@ __global__ void fx_vstat_final_kernel(int nb, double* __restrict__ part) {
 }
 
 bool fx_applicable(scdrs_ctx* c, int ncol, bool explicit_w) {
-    return c->spmm_mode != 1 && !explicit_w && ncol <= kFxMaxCol && c->nnz > 0;
+    // n_gene bounds the stored entries of a row, which keeps the 32-bit column totals exact (see the kernel)
+    return c->spmm_mode != 1 && !explicit_w && ncol <= kFxMaxCol && c->nnz > 0 && c->n_gene < (1 << 18);
 }
 
 // max and mean of |x * base_g| over the stored entries; c->gbase must hold the base weights of
@@ -385,6 +387,14 @@ __device__ __forceinline__ void fx_fma2(uint32_t acc_s, uint32_t both, float vs,
         : "memory");
 }
 
+// volatile, so that the compiler keeps the load where it is written (between the volatile
+// read-modify-writes) instead of sinking it towards its use
+__device__ __forceinline__ uint32_t fx_ldg_pinned(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // One warp per cell.  ginfo[g].meta = (first two-round block of gene g's list << 8) | number of blocks.
 //
 // The shared-memory work per list block is ~9 instructions, so everything around it is kept as lean
@@ -398,8 +408,11 @@ __device__ __forceinline__ void fx_fma2(uint32_t acc_s, uint32_t both, float vs,
 //   * the items flow through D register slots with no per-slot control flow: slot u is applied, then
 //     refilled with the list words of the item D positions later (one broadcast shared load, one
 //     global load), across chunk and pass-group boundaries.
+// Per-lane column totals are 32-bit: a flush moves word >> 12 into the total and leaves the low 12 bits
+// in the word (|sum over a row| < 2^18 entries * 2^25 / 2^12 = 2^31), which keeps the kernel at 96
+// registers = 20 warps per SM.
 template <bool WEIGHTED, int D>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kFxWarpsPerBlock * 32, kFxBlocksPerSM)
 spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict__ indptr,
                      const int32_t* __restrict__ indices, const float* __restrict__ data,
                      const GeneInfo* __restrict__ ginfo, const uint32_t* __restrict__ p_col32,
@@ -420,31 +433,18 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
     __syncwarp();
 
     for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell; row += (int64_t)gridDim.x * wpb) {
-        long long tot[kFxNB / 32];
+        int hi[kFxNB / 32];
 #pragma unroll
-        for (int t = 0; t < kFxNB / 32; ++t) tot[t] = 0;
-        // words -> 64-bit totals; lane l owns the columns j = 32 t + l (A in bank l, B in bank (l + t) % 32)
-        auto flush = [&]() {
-#pragma unroll
-            for (int t = 0; t < kFxNB / 32; ++t) {
-                if (t * 32 < ncol) {
-                    const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
-                    const int a = (int)accw[ia], b = (int)accw[ib];
-                    accw[ia] = 0u;
-                    accw[ib] = 0u;
-                    tot[t] += (long long)a + (long long)b;
-                }
-            }
-        };
+        for (int t = 0; t < kFxNB / 32; ++t) hi[t] = 0;
         // item slots, initially bubbles
         uint32_t s_ids[D];
         int s_x[D];
-        float2 s_w[D];
+        float2 s_w[WEIGHTED ? D : 1];
 #pragma unroll
         for (int u = 0; u < D; ++u) {
             s_ids[u] = trash_ids;
             s_x[u] = 0;
-            s_w[u] = make_float2(0.f, 0.f);
+            if (WEIGHTED) s_w[u] = make_float2(0.f, 0.f);
         }
         auto apply = [&](int u) {
             if (WEIGHTED)
@@ -453,7 +453,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                 fx_add2(acc_s, s_ids[u], s_x[u]);
         };
 
-        uint32_t bound = 0;
+        uint32_t lbound = 0;
         const int64_t p0 = indptr[row], p1 = indptr[row + 1];
         // chunk pipeline registers: record + value of the current chunk, ids + values of the next two
         int4 gi0 = make_int4(0, 0, 0, 0);
@@ -465,16 +465,15 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
             if (p0 + 32 + lane < p1) { idx1 = __ldg(indices + p0 + 32 + lane); dat1 = __ldg(data + p0 + 32 + lane); }
             if (idx0 >= 0) gi0 = __ldg(reinterpret_cast<const int4*>(ginfo + idx0));
         }
-        for (int64_t base = p0; base < p1; base += 32) {
-            // stage the loads of the chunks after this one
-            int4 gi1 = make_int4(0, 0, 0, 0);
-            if (idx1 >= 0) gi1 = __ldg(reinterpret_cast<const int4*>(ginfo + idx1));
-            idx2 = -1;
-            dat2 = 0.f;
-            if (base + 64 + lane < p1) { idx2 = __ldg(indices + base + 64 + lane); dat2 = __ldg(data + base + 64 + lane); }
-
+        for (int64_t base = p0;; base += 32) {
+            const bool done = base >= p1;
+            if (done) {
+                // drain the slots before the last flush
+#pragma unroll
+                for (int u = 0; u < D; ++u) apply(u);
+            }
             // this chunk: quantise, bound
-            const uint32_t meta = (uint32_t)gi0.z, nblk = meta & 255u, blk0 = meta >> 8;
+            const uint32_t meta = (uint32_t)gi0.z, nblk = done ? 0u : (meta & 255u), blk0 = meta >> 8;
             uint32_t qb = 0;
             int xq = 0;      // binary: the quantised entry; weighted: the bits of the scaled entry (float)
             if (nblk) {
@@ -488,35 +487,58 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                     qb = (uint32_t)(xq < 0 ? -xq : xq);
                 }
             }
-            const uint32_t csum = __reduce_add_sync(0xffffffffu, qb);
-            if (bound + csum >= kFxFlushAt) {     // warp-uniform
-                flush();
-                bound = kFxInflight;              // items still in the slots land after the flush
+            // Overflow guard without a warp reduction: every lane sums the bounds of its own entries; all
+            // lanes stay below 1/32 of the budget, so the sum over lanes (the true bound) stays below it.
+            // The one flush site: words -> totals, the low 12 bits stay in the word.  Lane l owns the
+            // columns j = 32 t + l (A in bank l, B in bank (l + t) % 32).
+            if (done || __any_sync(0xffffffffu, lbound + qb >= kFxFlushAt / 32u)) {
+#pragma unroll
+                for (int t = 0; t < kFxNB / 32; ++t) {
+                    if (t * 32 < ncol) {
+                        const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
+                        const int a = (int)accw[ia], b = (int)accw[ib];
+                        accw[ia] = (uint32_t)(a & 0xfff);
+                        accw[ib] = (uint32_t)(b & 0xfff);
+                        hi[t] += (a >> 12) + (b >> 12);
+                    }
+                }
+                lbound = kFxInflight / 32u + 4096u / 32u + 1u;   // slot items land after the flush; words keep 12 bits
             }
-            bound += csum;
-            const uint32_t maxblk = __reduce_max_sync(0xffffffffu, nblk);
-            for (uint32_t pg = 0; pg < maxblk; pg += 4) {
+            if (done) break;
+            lbound += qb;
+
+            // stage the loads of the chunks after this one
+            int4 gi1 = make_int4(0, 0, 0, 0);
+            if (idx1 >= 0) gi1 = __ldg(reinterpret_cast<const int4*>(ginfo + idx1));
+            idx2 = -1;
+            dat2 = 0.f;
+            if (base + 64 + lane < p1) { idx2 = __ldg(indices + base + 64 + lane); dat2 = __ldg(data + base + 64 + lane); }
+
+            for (uint32_t pg = 0;; pg += 4) {
                 // compact the items of passes pg .. pg+3 into shared memory
+                uint32_t m = __ballot_sync(0xffffffffu, nblk > pg);
+                if (m == 0u) break;
                 __syncwarp();
                 uint32_t n_items = 0;
 #pragma unroll
                 for (uint32_t dp = 0; dp < 4; ++dp) {
                     const uint32_t pass = pg + dp;
-                    const bool has = nblk > pass;
-                    const uint32_t m = __ballot_sync(0xffffffffu, has);
-                    if (has) items[n_items + __popc(m & lt_mask)] = make_uint2(blk0 + pass, (uint32_t)xq);
+                    if (dp > 0) m = __ballot_sync(0xffffffffu, nblk > pass);
+                    if (nblk > pass) items[n_items + __popc(m & lt_mask)] = make_uint2(blk0 + pass, (uint32_t)xq);
                     n_items += __popc(m);
                 }
                 if (lane < D) items[n_items + lane] = make_uint2(0u, 0u);   // bubbles
                 __syncwarp();
 #pragma unroll 1
                 for (uint32_t i = 0; i < n_items; i += D) {
+                    uint2 itn = items[i];                                // broadcast
 #pragma unroll
                     for (int u = 0; u < D; ++u) {
+                        const uint2 it = itn;
+                        if (u + 1 < D) itn = items[i + u + 1];           // in flight while slot u is applied
                         apply(u);
-                        const uint2 it = items[i + u];                   // broadcast
                         const uint32_t t = it.x * 32u + lane;
-                        s_ids[u] = __ldg(p_col32 + t);
+                        s_ids[u] = fx_ldg_pinned(p_col32 + t);           // D items before its use
                         if (WEIGHTED) s_w[u] = __ldg(p_val2 + t);
                         s_x[u] = (int)it.y;
                     }
@@ -527,37 +549,49 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
             idx1 = idx2;
             dat1 = dat2;
         }
-        // drain
-#pragma unroll
-        for (int u = 0; u < D; ++u) apply(u);
-        flush();
-        // epilogue: column scale, covariate terms, row reference, deviations
-        double rs = 0.0;
+        // Fold the totals into the words (A: total >> 12, B: the low 12 bits), so that the epilogue can
+        // walk the columns with a rolled loop (dynamic shared addresses instead of 32 unrolled copies).
 #pragma unroll
         for (int t = 0; t < kFxNB / 32; ++t) {
-            const int j = t * 32 + lane;
-            if (j < ncol) {
-                double v = ((double)tot[t] * inv_scale) * colscale[j];
-                if (k > 0) {
-                    double cterm = covm[j];
-                    for (int kk = 0; kk < k; ++kk)
-                        cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
-                    v += cterm;
-                }
-                tot[t] = __double_as_longlong(v);
-                rs += v;
+            if (t * 32 < ncol) {
+                const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
+                const int lo = (int)accw[ia] + (int)accw[ib];      // two 12-bit residues
+                accw[ia] = (uint32_t)(hi[t] + (lo >> 12));
+                accw[ib] = (uint32_t)(lo & 0xfff);
             }
+        }
+        // epilogue: column scale, covariate terms, row reference, deviations; two passes, the values
+        // are recomputed bit for bit instead of being held in 64 registers
+        auto column_value = [&](int t, int j) -> double {
+            const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
+            const long long total = ((long long)(int)accw[ia] << 12) + (long long)accw[ib];
+            double v = ((double)total * inv_scale) * colscale[j];
+            if (k > 0) {
+                double cterm = covm[j];
+                for (int kk = 0; kk < k; ++kk)
+                    cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
+                v += cterm;
+            }
+            return v;
+        };
+        double rs = 0.0;
+#pragma unroll 1
+        for (int t = 0; t * 32 < ncol; ++t) {
+            const int j = t * 32 + lane;
+            if (j < ncol) rs += column_value(t, j);
         }
         rs = fx_warp_sum(rs);
         const double ref = rs / (double)ncol;
         float* out = dev_mat + row * (int64_t)ld;
-#pragma unroll
-        for (int t = 0; t < kFxNB / 32; ++t) {
+#pragma unroll 1
+        for (int t = 0; t * 32 < ncol; ++t) {
             const int j = t * 32 + lane;
             if (j < ncol) {
-                const double v = __longlong_as_double(tot[t]);
+                const double v = column_value(t, j);
                 out[j] = (v == 0.0) ? __int_as_float(0x7fc00000) : (float)(v - ref);
             }
+            accw[t * 32 + lane] = 0u;
+            accw[kFxNB + t * 32 + ((lane + t) & 31)] = 0u;
         }
         if (lane == 0) row_ref[row] = ref;
     }
@@ -570,7 +604,7 @@ int fx_spmm(scdrs_ctx* c) {
     SCDRS_CHECK(c->w_fx && ncol <= kFxMaxCol, "fixed-point lists were not built");
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
-    const int wpb = 8, per_sm = 2;
+    const int wpb = kFxWarpsPerBlock, per_sm = kFxBlocksPerSM;
     const size_t smem = (size_t)kFxWarpBytes * wpb;
     static bool attr_set = false;
     if (!attr_set) {
