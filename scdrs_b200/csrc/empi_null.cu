@@ -173,7 +173,7 @@ __global__ void make_keys_kernel(int64_t m, const F* __restrict__ q,
 }
 
 // ---- LSD radix sort: one warp per chunk of kChunk keys ------------------------------------------
-constexpr int kChunk = 2048;
+constexpr int kChunk = 512;
 constexpr int kSortWarps = 4;
 
 template <typename K>
@@ -297,17 +297,21 @@ __global__ void grid_params_kernel(int64_t m, int n_cells, const typename KeyOf<
 }
 
 // grid[c] = number of sorted queries whose cell is < c, for c in [0, n_cells]
+// one thread per grid cell: binary search over the sorted queries (their cell index is monotone)
 template <typename F>
 __global__ void grid_build_kernel(int64_t m, int n_cells, const typename KeyOf<F>::type* __restrict__ keys,
                                   const F* __restrict__ params, uint32_t* __restrict__ grid) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= m) return;
+    const int64_t cc = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cc > n_cells) return;
     const F lo = params[0], scale = params[1];
-    const int cs = grid_cell<F>(key_to_float<F>(keys[s]), lo, scale, n_cells);
-    const int cp = s > 0 ? grid_cell<F>(key_to_float<F>(keys[s - 1]), lo, scale, n_cells) : -1;
-    for (int cc = cp + 1; cc <= cs; ++cc) grid[cc] = (uint32_t)s;
-    if (s == m - 1)
-        for (int cc = cs + 1; cc <= n_cells; ++cc) grid[cc] = (uint32_t)m;
+    int64_t a = 0, b = m;
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        const F q = key_to_float<F>(keys[mid]);     // NaN queries sort last: treat them as beyond the grid
+        const int64_t qc = (q != q) ? (int64_t)n_cells + 1 : grid_cell<F>(q, lo, scale, n_cells);
+        if (qc < cc) a = mid + 1; else b = mid;
+    }
+    grid[cc] = (uint32_t)a;
 }
 
 // number of sorted queries <= v
@@ -350,7 +354,7 @@ static int prepare_queries(scdrs_ctx* c, const F* dev_q, int64_t m, int* sorted_
     F* params = reinterpret_cast<F*>(c->scalars.as<double>() + 2);
     grid_params_kernel<F><<<1, 1, 0, c->stream>>>(m, n_cells, c->sort_keys[*sorted_buf].as<K>(), params);
     SCDRS_LAUNCH_CHECK(c);
-    grid_build_kernel<F><<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(
+    grid_build_kernel<F><<<(unsigned)((n_cells + 256) / 256), 256, 0, c->stream>>>(
         m, n_cells, c->sort_keys[*sorted_buf].as<K>(), params, c->grid.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     return 0;

@@ -121,7 +121,7 @@ int fx_value_stats(scdrs_ctx* c, int weight_opt) {
 constexpr int kAsgThreads = 64;
 constexpr int kAsgMaxLen = 128;
 constexpr int kAsgMaxR = 8;
-constexpr int kAsgBytesPerThread = 32 * kAsgMaxR + 32 + 32 + 32 + kAsgMaxLen / 8 + 64;
+constexpr int kAsgBytesPerThread = 2 * 32 * kAsgMaxR + 32 + 32 + 32 + 64;
 
 __global__ void __launch_bounds__(kAsgThreads)
 fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t* __restrict__ w_col,
@@ -129,20 +129,15 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
     extern __shared__ unsigned char asg_sm[];
     constexpr int T = kAsgThreads;
     const int tid = threadIdx.x;
-    unsigned char* sm_slot = asg_sm;                              // [32 * kAsgMaxR][T]
-    unsigned char* sm_par = sm_slot + 32 * kAsgMaxR * T;          // [32][T]
+    unsigned char* sm_slot = asg_sm;                              // [32 * kAsgMaxR][T] entry in the slot
+    unsigned char* sm_alt = sm_slot + 32 * kAsgMaxR * T;          // [32 * kAsgMaxR][T] its other bank
+    unsigned char* sm_par = sm_alt + 32 * kAsgMaxR * T;           // [32][T]
     unsigned char* sm_via = sm_par + 32 * T;                      // [32][T]
     unsigned char* sm_que = sm_via + 32 * T;                      // [32][T]
-    unsigned char* sm_side = sm_que + 32 * T;                     // [kAsgMaxLen / 8][T]
-    unsigned short* sm_load = reinterpret_cast<unsigned short*>(sm_side + (kAsgMaxLen / 8) * T);  // [32][T]
+    unsigned short* sm_load = reinterpret_cast<unsigned short*>(sm_que + 32 * T);  // [32][T]
 #define FX_SLOT(b, k) sm_slot[((b) * kAsgMaxR + (k)) * T + tid]
+#define FX_ALT(b, k) sm_alt[((b) * kAsgMaxR + (k)) * T + tid]
 #define FX_LOAD(b) sm_load[(b) * T + tid]
-#define FX_SIDE_GET(i) ((sm_side[((i) >> 3) * T + tid] >> ((i) & 7)) & 1u)
-#define FX_SIDE_SET(i, v)                                                              \
-    do {                                                                               \
-        unsigned char& by__ = sm_side[((i) >> 3) * T + tid];                           \
-        by__ = (unsigned char)((by__ & ~(1u << ((i) & 7))) | ((uint32_t)(v) << ((i) & 7))); \
-    } while (0)
     const int g = blockIdx.x * T + tid;
     if (g >= n_gene) return;
     if (g == 0) rounds[n_gene] = 0;
@@ -156,20 +151,22 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
     bool greedy = n > (uint32_t)kAsgMaxLen;
     uint32_t R = (n + 31u) >> 5;
     if (!greedy) {
+        uint32_t jn = w_col[s];
         for (uint32_t t = 0; t < n; ++t) {
-            const uint32_t j = w_col[s + t];
+            const uint32_t j = jn;
+            if (t + 1 < n) jn = w_col[s + t + 1];
             const uint32_t a = fx_bank_a(j), b = fx_bank_b(j);
             const uint32_t la = FX_LOAD(a), lb = FX_LOAD(b);
             if (la < R && (la <= lb || lb >= R)) {
                 FX_SLOT(a, la) = (unsigned char)t;
+                FX_ALT(a, la) = (unsigned char)b;
                 FX_LOAD(a) = (unsigned short)(la + 1);
-                FX_SIDE_SET(t, 0u);
                 continue;
             }
             if (lb < R) {
                 FX_SLOT(b, lb) = (unsigned char)t;
+                FX_ALT(b, lb) = (unsigned char)a;
                 FX_LOAD(b) = (unsigned short)(lb + 1);
-                FX_SIDE_SET(t, 1u);
                 continue;
             }
             // both banks full: breadth-first search for a bank with a free slot
@@ -186,10 +183,8 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
                 const uint32_t cb = sm_que[(qh++) * T + tid];
                 const uint32_t lcb = FX_LOAD(cb);
                 for (uint32_t k = 0; k < lcb; ++k) {
-                    const uint32_t i = FX_SLOT(cb, k);
-                    const uint32_t ji = w_col[s + i];
-                    const uint32_t alt = FX_SIDE_GET(i) ? fx_bank_a(ji) : fx_bank_b(ji);
-                    if (alt == cb || ((visited >> alt) & 1u)) continue;
+                    const uint32_t alt = FX_ALT(cb, k);
+                    if ((visited >> alt) & 1u) continue;     // covers alt == cb
                     visited |= 1u << alt;
                     sm_par[alt * T + tid] = (unsigned char)cb;
                     sm_via[alt * T + tid] = (unsigned char)k;
@@ -203,8 +198,8 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
             if (target < 0) {
                 if (R < (uint32_t)kAsgMaxR) {     // no augmenting path: one more round
                     FX_SLOT(a, la) = (unsigned char)t;
+                    FX_ALT(a, la) = (unsigned char)b;
                     FX_LOAD(a) = (unsigned short)(la + 1);
-                    FX_SIDE_SET(t, 0u);
                     ++R;
                     continue;
                 }
@@ -216,15 +211,14 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
             FX_LOAD(hb) = (unsigned short)(hk + 1);
             while (sm_par[cur * T + tid] != ROOT) {
                 const uint32_t p = sm_par[cur * T + tid], k = sm_via[cur * T + tid];
-                const uint32_t i = FX_SLOT(p, k);
-                FX_SLOT(hb, hk) = (unsigned char)i;
-                FX_SIDE_SET(i, FX_SIDE_GET(i) ^ 1u);
+                FX_SLOT(hb, hk) = FX_SLOT(p, k);
+                FX_ALT(hb, hk) = (unsigned char)p;
                 hb = p;
                 hk = k;
                 cur = p;
             }
             FX_SLOT(hb, hk) = (unsigned char)t;
-            FX_SIDE_SET(t, hb == a ? 0u : 1u);
+            FX_ALT(hb, hk) = (unsigned char)(hb == a ? b : a);
         }
     }
     uint32_t rmax = 0;
@@ -234,7 +228,8 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
             rmax = lb > rmax ? lb : rmax;
             for (uint32_t k = 0; k < lb; ++k) {
                 const uint32_t i = FX_SLOT(b, k);
-                code[s + i] = (uint16_t)((k << 1) | FX_SIDE_GET(i));
+                const uint32_t side = fx_bank_a(w_col[s + i]) == b ? 0u : 1u;
+                code[s + i] = (uint16_t)((k << 1) | side);
             }
         }
     } else {
@@ -256,9 +251,8 @@ fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t*
     }
     rounds[g] = rmax;
 #undef FX_SLOT
+#undef FX_ALT
 #undef FX_LOAD
-#undef FX_SIDE_GET
-#undef FX_SIDE_SET
 }
 
 // padded list length in 16-bit entries: blocks of two rounds x 32 lanes
