@@ -415,8 +415,11 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_ms,
                 "scatter_fma_per_launch": float(nnz) * (1 + n_ctrl) * args.n_trait_gene / args.n_gene,
-                "note": "bound by the shared-memory/L1 data pipe (75% busy in ncu: one 64-bit load+store per "
-                        "accumulate, 1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4"}
+                "note": ("bound by the LSU / shared-memory data pipe (86% busy in ncu: one conflict-free 32-bit load + "
+                         "store per accumulate, 1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4")
+                if spmm_kind == "fixed" else
+                ("bound by the shared-memory/L1 data pipe (89% busy in ncu: one 64-bit load+store per accumulate, "
+                 "1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4")}
 
     # ---- end to end through the public API with host inputs
     e2e = None
@@ -453,7 +456,8 @@ def main():
             "metric": "cell x trait scores/sec at n_ctrl=%d" % n_ctrl, "value": value, "unit": "cell*trait/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "vs_baseline": None, "dtype": "s32 fixed point (exact sums) + f64" if spmm_kind == "fixed" else "f64",
+            "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "setup": info,
             "device_ms_per_trait": 1e3 * wall / args.steps / len(names), "wall_s_check": wall_check,
