@@ -326,6 +326,14 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     adata, traits, info = build_workload(args, rank, device)
+    if world > 1:
+        # One atlas, cells sharded: the gene-level parameters (GENE_STATS incl. the mean_var bins,
+        # COV_BETA, COV_GENE_MEAN) must be the same on every rank or the ranks would draw different
+        # control sets.  The bench takes rank 0's (a distributed preprocess is outside this bench).
+        keys = ["GENE_STATS", "COV_BETA", "COV_GENE_MEAN"]
+        box = [{k: adata.uns["SCDRS_PARAM"][k] for k in keys} if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        adata.uns["SCDRS_PARAM"].update(box[0])
     names = list(traits)
     n_cell, n_ctrl = args.n_cell, args.n_ctrl
     state = _device.get_state(adata)
@@ -423,25 +431,30 @@ def main():
 
     # ---- end to end through the public API with host inputs
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         def e2e_step():
             scdrs_b200.clear_device_cache()
-            res = scdrs_b200.score_traits(adata, traits, n_ctrl=n_ctrl)
+            res = scdrs_b200.score_traits(adata, traits, n_ctrl=n_ctrl, sharded=world > 1)
             return res
         e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 2))
         for _ in range(n_e2e):
             res = e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t_e2e = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            dt = float(t_e2e.item())
         st = _device.get_state(adata)
         h2d = st.h2d_bytes + len(names) * (preps[0]["ctrl_cols"].nbytes + 3 * 8 * args.n_trait_gene + 2 * 8 * args.n_gene)
         d2h = len(names) * n_cell * (8 + 4 + 4 + 8)
-        e2e = {"value": n_cell * len(names) / dt, "unit": "cell*trait/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "s_per_step": dt,
-               "api": "scdrs_b200.score_traits (score_cell per trait, host control-gene draws overlapped)"}
+        e2e = {"value": total_cells * len(names) / dt, "unit": "cell*trait/s", "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "s_per_step": dt,
+               "api": "scdrs_b200.score_traits (score_cell per trait, host control-gene draws overlapped)"
+                      + ("; one process per GPU, sharded=True" if world > 1 else "")}
         del res
 
     cpu = None

@@ -357,8 +357,14 @@ def score_traits(
     min_genes=0,
     n_jobs=None,
     on_result=None,
+    sharded=False,
 ):
     """Score every gene set of ``dict_gs`` = {trait: (gene_list, gene_weight_list)}.
+
+    ``sharded=True`` (one process per GPU under torchrun, ``torch.distributed`` initialised):
+    ``data`` holds this rank's block of cells; the gene-set alignment statistics and the pooled
+    empirical null span the cells of all ranks (``scdrs_b200.distributed.ShardedScorer``), every
+    rank draws the same control sets, and the returned frames cover this rank's cells.
 
     Each trait gets exactly what ``score_cell`` would return for it (every call re-seeds, so traits
     are independent, scdrs/method.py:96, :276); the host work of upcoming traits (gene
@@ -401,6 +407,16 @@ def score_traits(
         ctx = state.ensure_matrix(adata)
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
+        if sharded:
+            import torch
+
+            from .distributed import CudaPhases, ShardedScorer
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            scorer = ShardedScorer(CudaPhases(ctx, dev), dev)
+            score_one = scorer.score
+        else:
+            score_one = ctx.score_trait
         pending = []          # (trait, future of the result frame): frames are built off the critical path
 
         def drain(limit):
@@ -414,9 +430,9 @@ def score_traits(
 
         for t in traits:
             prep = futs.pop(t).result()
-            out = ctx.score_trait(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
-                                  weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
-                                  want_ctrl_norm=return_ctrl_norm_score)
+            out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
+                            weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
+                            want_ctrl_norm=return_ctrl_norm_score)
             pending.append((t, frame_pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
                                            return_ctrl_norm_score)))
             drain(2)
