@@ -572,3 +572,30 @@ def test_fixed_point_scatter_falls_back_on_outliers_and_wide_matrices(native_lib
     df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=50)
     assert kind[0] == "f64"
     _compare_with_reference(df, ref, 50, 300)
+
+
+def test_score_traits_equal_score_cell(native_lib):
+    """score_traits (host work of upcoming traits in worker threads, frames built off the critical
+    path): every frame must equal, bit for bit, what score_cell returns for that trait alone, in
+    .gs order, with binary and weighted traits mixed."""
+    import scdrs_b200
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(900, 2500, density=0.1, seed=21)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    traits = synth.make_traits(adata.var_names, 5, 150, weighted=False, seed=40)
+    traits.update({"w_" + k: v for k, v in synth.make_traits(adata.var_names, 4, 120, weighted=True, seed=50).items()})
+    seen = []
+    res = scdrs_b200.score_traits(adata, traits, n_ctrl=200, return_ctrl_norm_score=True,
+                                  on_result=lambda t, df: seen.append((t, df)))
+    assert res == list(traits) and [t for t, _ in seen] == list(traits)
+    for t, df in seen:
+        genes, w = traits[t]
+        one = scdrs_b200.score_cell(adata, genes, gene_weight=w, n_ctrl=200, return_ctrl_norm_score=True)
+        assert np.array_equal(df.values, one.values, equal_nan=True), t
+    # an error inside a worker thread surfaces in the caller
+    bad = dict(traits)
+    bad["broken"] = (["not_a_gene"], [1.0])
+    with pytest.raises(Exception):
+        scdrs_b200.score_traits(adata, bad, n_ctrl=20)
