@@ -68,7 +68,7 @@ static void release_all(scdrs_ctx* c) {
                       &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
-                      &c->w_code, &c->w_rounds, &c->fx_part};
+                      &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -227,6 +227,7 @@ int scdrs_set_csr_host(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64
     c->trait_ready = false;
     c->have_stats = false;
     c->fx_stat_key = -1;
+    c->tile_ptr_valid = false;
     c->k = 0;
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -249,6 +250,7 @@ int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_
     c->trait_ready = false;
     c->have_stats = false;
     c->fx_stat_key = -1;
+    c->tile_ptr_valid = false;
     c->k = 0;
     return 0;
 }

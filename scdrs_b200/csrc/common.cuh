@@ -63,6 +63,8 @@ struct scdrs_ctx {
     const int32_t* indices = nullptr;
     const float* data = nullptr;
     scdrs::DevBuf own_indptr, own_indices, own_data;
+    scdrs::DevBuf tile_ptr;        // where every gene tile starts inside every CSR row (stats.cu)
+    bool tile_ptr_valid = false;
 
     // gene-level vectors
     scdrs::DevBuf var, var_tech;

@@ -32,82 +32,193 @@ __device__ __forceinline__ double warp_sum_s(double v) {
 // kRowTile x kGeneTile dense tiles of X in shared memory (rows are located by binary search in the
 // sorted CSR column ids).  v = (x + sum_k C[c,k] B[g,k]) + mu with the k-sum accumulated in index
 // order by fma, as a BLAS dgemm micro-kernel does.  Bitwise reproducible.
-constexpr int kGeneTile = 64;    // 313 tiles at 20k genes: ~2 resident CTAs per SM, no tail wave
+constexpr int kGeneTile = 32;    // 626 tiles at 20k genes: ~4 resident CTAs per SM (each is one latency chain)
 constexpr int kRowTile = 64;
+constexpr int kStatThreadsSeq = 2 * kGeneTile;   // consumers (one per gene) + producers (one per staged row)
+
+// tptr[t][r] = number of stored entries of row r with column < t * kGeneTile (t = 0 .. n_tile): where
+// a gene tile starts inside every CSR row.  Built once per matrix by one warp per row; it replaces an
+// 11-step dependent binary search per (row, tile) by one coalesced load.
+__global__ void __launch_bounds__(256)
+tile_ptr_kernel(int64_t n_cell, int n_tile, const int64_t* __restrict__ indptr,
+                const int32_t* __restrict__ indices, uint32_t* __restrict__ tptr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp0; row < n_cell; row += nwarp) {
+        const int64_t p0 = indptr[row], p1 = indptr[row + 1];
+        const int64_t len = p1 - p0;
+        // entry i opens the tiles (tile(i-1), tile(i)]; the tail (tile(last), n_tile] gets len
+        for (int64_t i = lane; i <= len; i += 32) {
+            const int prev = i > 0 ? indices[p0 + i - 1] / kGeneTile : -1;
+            const int cur = i < len ? indices[p0 + i] / kGeneTile : n_tile;
+            for (int t = prev + 1; t <= cur; ++t) tptr[(size_t)t * n_cell + row] = (uint32_t)i;
+        }
+    }
+}
+
+static int ensure_tile_ptr(scdrs_ctx* c) {
+    const int n_tile = (c->n_gene + kGeneTile - 1) / kGeneTile;
+    const size_t bytes = (size_t)(n_tile + 1) * c->n_cell * sizeof(uint32_t);
+    if (bytes > ((size_t)6 << 30)) {      // too large to be worth it: the kernels fall back to searching
+        c->tile_ptr_valid = false;
+        return 0;
+    }
+    if (c->tile_ptr_valid) return 0;
+    SCDRS_TRY(c->tile_ptr.reserve(bytes));
+    int64_t grid = (c->n_cell + 7) / 8;
+    if (grid > kNumSM * 8) grid = kNumSM * 8;
+    tile_ptr_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(c->n_cell, n_tile, c->indptr, c->indices,
+                                                          c->tile_ptr.as<uint32_t>());
+    SCDRS_LAUNCH_CHECK(c);
+    c->tile_ptr_valid = true;
+    return 0;
+}
+
+// Fill rows [0, nr) of a dense tile (cells r0.., genes g0 .. g0 + kGeneTile) of X from the CSR rows; the
+// calling threads (tid of nthreads) take rows round-robin.  The loads of a row segment are issued four
+// at a time (their addresses are known up front), so a segment costs one memory round trip, not one per
+// stored entry.
+__device__ __forceinline__ void stage_rows(float (*buf)[kGeneTile + 1], int tid, int nthreads, int64_t r0, int nr,
+                                           int g0, int tile_id, int64_t n_cell,
+                                           const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                           const float* __restrict__ data, const uint32_t* __restrict__ tptr) {
+    for (int rr = tid; rr < nr; rr += nthreads) {
+        const int64_t row = r0 + rr;
+        const int64_t p0 = indptr[row];
+        int64_t lo, hi;
+        if (tptr != nullptr) {
+            lo = p0 + tptr[(size_t)tile_id * n_cell + row];
+            hi = p0 + tptr[(size_t)(tile_id + 1) * n_cell + row];
+        } else {
+            const int64_t p1 = indptr[row + 1];
+            lo = p0;
+            hi = p1;
+            while (lo < hi) {                     // first stored column >= g0
+                const int64_t mid = (lo + hi) >> 1;
+                if (indices[mid] < g0) lo = mid + 1; else hi = mid;
+            }
+            hi = p1;
+        }
+        bool more = true;
+        for (int64_t t = lo; t < hi && more; t += 4) {
+            int col[4];
+            float val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool in = t + u < hi;
+                col[u] = in ? indices[t + u] - g0 : kGeneTile;
+                val[u] = in ? data[t + u] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (col[u] < kGeneTile) buf[rr][col[u]] = val[u];
+                else more = false;                // past the tile (only reachable without the table) or past hi
+            }
+        }
+    }
+}
+
+// Producer side of the two-group kernels: the threads [kGeneTile, 2 kGeneTile) fill one tile.
+__device__ __forceinline__ void stage_tile(float (*buf)[kGeneTile + 1], int ptid, int64_t r0, int nr, int g0,
+                                           int tile_id, int64_t n_cell, const int64_t* __restrict__ indptr,
+                                           const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                           const uint32_t* __restrict__ tptr) {
+    for (int i = ptid; i < kRowTile * (kGeneTile + 1); i += kGeneTile) (&buf[0][0])[i] = 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(kGeneTile));      // producers only
+    stage_rows(buf, ptid, kGeneTile, r0, nr, g0, tile_id, n_cell, indptr, indices, data, tptr);
+}
+
+// Work split inside a CTA (kGeneTile genes): the transform T(x + C.B + mu) of every (cell, gene) pair is
+// independent and goes to the "transform" warps, which also stage the tiles of X; only the summation
+// has to be sequential, and the "owner" warp (one thread per gene) does nothing else: one shared
+// load and one add per cell.  Tiles of kSeqRows cells are double-buffered between the two groups.
+constexpr int kSeqRows = 32;
+constexpr int kSeqThreads = 128;
+constexpr int kSeqXform = kSeqThreads - kGeneTile;   // transform threads
 
 template <int TRANSFORM>
-__global__ void __launch_bounds__(kGeneTile)
+__global__ void __launch_bounds__(kSeqThreads)
 stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double denom,
                       const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                      const float* __restrict__ data, const double* __restrict__ cov_mat,
+                      const float* __restrict__ data, const uint32_t* __restrict__ tptr,
+                      const double* __restrict__ cov_mat,
                       const double* __restrict__ cov_beta, const double* __restrict__ gene_mean,
                       const double* __restrict__ cell_w, double* __restrict__ gsum,
                       double* __restrict__ gsq) {
-    extern __shared__ double sdyn[];                 // [k][kGeneTile] covariate effects of this tile
-    __shared__ float tile[kRowTile][kGeneTile + 1];
+    extern __shared__ double sdyn[];                 // [k][kGeneTile] covariate effects, then [kGeneTile] mu
+    __shared__ float xt[kSeqRows][kGeneTile + 1];
+    __shared__ double tt[2][kSeqRows][kGeneTile];
+    const bool owner = threadIdx.x < kGeneTile;
     const int g0 = blockIdx.x * kGeneTile;
-    const int g = g0 + threadIdx.x;
-    const bool ok = g < n_gene;
-    for (int kk = 0; kk < k; ++kk) sdyn[kk * kGeneTile + threadIdx.x] = ok ? cov_beta[(size_t)g * k + kk] : 0.0;
-    const double mu = (ok && k > 0) ? gene_mean[g] : 0.0;
+    const int g = g0 + (int)threadIdx.x;
+    const bool ok = owner && g < n_gene;
+    double* smu = sdyn + (size_t)k * kGeneTile;
+    if (owner) {
+        for (int kk = 0; kk < k; ++kk) sdyn[kk * kGeneTile + threadIdx.x] = g < n_gene ? cov_beta[(size_t)g * k + kk] : 0.0;
+        smu[threadIdx.x] = (g < n_gene && k > 0) ? gene_mean[g] : 0.0;
+    }
+    __syncthreads();
+    const int xid = (int)threadIdx.x - kGeneTile;    // 0 .. kSeqXform-1 for the transform threads
+    const int64_t n_rt = (n_cell + kSeqRows - 1) / kSeqRows;
+
+    // transform threads: stage the X tile of row tile rt, then write T(v) for all its pairs into tt[buf]
+    auto produce = [&](int64_t rt, int buf) {
+        const int64_t r0 = rt * kSeqRows;
+        const int nr = (int)((n_cell - r0) < kSeqRows ? (n_cell - r0) : kSeqRows);
+        for (int i = xid; i < kSeqRows * (kGeneTile + 1); i += kSeqXform) (&xt[0][0])[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kSeqXform));
+        stage_rows(xt, xid, kSeqXform, r0, nr, g0, blockIdx.x, n_cell, indptr, indices, data, tptr);
+        asm volatile("bar.sync 1, %0;" ::"n"(kSeqXform));
+        for (int p = xid; p < nr * kGeneTile; p += kSeqXform) {
+            const int r = p / kGeneTile, gi = p % kGeneTile;
+            double v = (double)xt[r][gi];
+            if (k > 0) {
+                const double* crow = cov_mat + (r0 + r) * k;
+                double cb = crow[0] * sdyn[gi];
+                for (int kk = 1; kk < k; ++kk) cb = fma(crow[kk], sdyn[kk * kGeneTile + gi], cb);
+                v = (v + cb) + smu[gi];
+            }
+            tt[buf][r][gi] = apply_t<TRANSFORM>(v);
+        }
+    };
+
     const int n_pass = center ? 2 : 1;
     double s = 0.0, q = 0.0, mean = 0.0;
     for (int pass = 0; pass < n_pass; ++pass) {
-        for (int64_t r0 = 0; r0 < n_cell; r0 += kRowTile) {
-            const int nr = (int)((n_cell - r0) < kRowTile ? (n_cell - r0) : kRowTile);
-            __syncthreads();
-            for (int i = threadIdx.x; i < kRowTile * (kGeneTile + 1); i += kGeneTile) (&tile[0][0])[i] = 0.f;
-            __syncthreads();
-            if ((int)threadIdx.x < nr) {
-                const int64_t p0 = indptr[r0 + threadIdx.x], p1 = indptr[r0 + threadIdx.x + 1];
-                int64_t lo = p0, hi = p1;
-                while (lo < hi) {                     // first stored column >= g0
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (indices[mid] < g0) lo = mid + 1; else hi = mid;
-                }
-                for (int64_t t = lo; t < p1; ++t) {
-                    const int col = indices[t] - g0;
-                    if (col >= kGeneTile) break;
-                    tile[threadIdx.x][col] = data[t];
-                }
-            }
-            __syncthreads();
-            if (ok) {
-                // four cells at a time: the transforms are independent (instruction-level parallelism),
-                // the accumulation stays strictly in cell order
-                for (int rb = 0; rb < nr; rb += 4) {
-                    double t[4], w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = rb + u < nr ? rb + u : nr - 1;
-                        double v = (double)tile[r][threadIdx.x];
-                        if (k > 0) {
-                            const double* crow = cov_mat + (r0 + r) * k;
-                            double cb = crow[0] * sdyn[threadIdx.x];
-                            for (int kk = 1; kk < k; ++kk) cb = fma(crow[kk], sdyn[kk * kGeneTile + threadIdx.x], cb);
-                            v = (v + cb) + mu;
+        if (!owner) produce(0, 0);
+        __syncthreads();
+        for (int64_t rt = 0; rt < n_rt; ++rt) {
+            if (!owner) {
+                if (rt + 1 < n_rt) produce(rt + 1, (int)((rt + 1) & 1));
+            } else if (ok) {
+                const int64_t r0 = rt * kSeqRows;
+                const int nr = (int)((n_cell - r0) < kSeqRows ? (n_cell - r0) : kSeqRows);
+                const double (*cur)[kGeneTile] = tt[rt & 1];
+                // strictly in cell order; explicit _rn intrinsics: no fma contraction, numpy multiplies then adds
+                if (pass == 0) {
+                    if (cell_w == nullptr) {
+                        for (int r = 0; r < nr; ++r) {
+                            const double t = cur[r][threadIdx.x];
+                            s = __dadd_rn(s, t);
+                            if (!center) q = __dadd_rn(q, __dmul_rn(t, t));
                         }
-                        t[u] = apply_t<TRANSFORM>(v);
-                        w[u] = cell_w != nullptr ? cell_w[r0 + r] : 1.0;
+                    } else {
+                        for (int r = 0; r < nr; ++r) {
+                            const double t = cur[r][threadIdx.x], w = cell_w[r0 + r];
+                            s = __dadd_rn(s, __dmul_rn(t, w));
+                            if (!center) q = __dadd_rn(q, __dmul_rn(__dmul_rn(t, t), w));
+                        }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (rb + u >= nr) break;
-                        // explicit _rn intrinsics: no fma contraction, numpy multiplies then adds
-                        if (pass == 0) {
-                            s = __dadd_rn(s, cell_w != nullptr ? __dmul_rn(t[u], w[u]) : t[u]);
-                            if (!center) {
-                                const double t2 = __dmul_rn(t[u], t[u]);
-                                q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(t2, w[u]) : t2);
-                            }
-                        } else {
-                            const double d = __dadd_rn(t[u], -mean);
-                            const double d2 = __dmul_rn(d, d);
-                            q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(d2, w[u]) : d2);
-                        }
+                } else {
+                    for (int r = 0; r < nr; ++r) {
+                        const double d = __dadd_rn(cur[r][threadIdx.x], -mean);
+                        const double d2 = __dmul_rn(d, d);
+                        q = __dadd_rn(q, cell_w != nullptr ? __dmul_rn(d2, cell_w[r0 + r]) : d2);
                     }
                 }
             }
+            __syncthreads();
         }
         if (pass == 0) mean = s / denom;
     }
@@ -124,41 +235,40 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
 // in float64 in cell order (multiply, then add), as scipy's csc_matvecs does.
 constexpr int kMaxCovReg = 16;
 
-__global__ void __launch_bounds__(kGeneTile)
+__global__ void __launch_bounds__(kStatThreadsSeq)
 gene_mean_xtc_kernel(int64_t n_cell, int n_gene, int k, float inv_n,
                      const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                     const float* __restrict__ data, const double* __restrict__ cov_mat,
+                     const float* __restrict__ data, const uint32_t* __restrict__ tptr,
+                     const double* __restrict__ cov_mat,
                      float* __restrict__ gmean32, double* __restrict__ xtc) {
-    __shared__ float tile[kRowTile][kGeneTile + 1];
+    __shared__ float tile[2][kRowTile][kGeneTile + 1];
+    const bool producer = threadIdx.x >= kGeneTile;
+    const int tid = threadIdx.x & (kGeneTile - 1);
     const int g0 = blockIdx.x * kGeneTile;
-    const int g = g0 + threadIdx.x;
-    const bool ok = g < n_gene;
+    const int g = g0 + tid;
+    const bool ok = !producer && g < n_gene;
     float s32 = 0.f;
     double acc[kMaxCovReg];
 #pragma unroll
     for (int kk = 0; kk < kMaxCovReg; ++kk) acc[kk] = 0.0;
-    for (int64_t r0 = 0; r0 < n_cell; r0 += kRowTile) {
+    const int64_t n_rt = (n_cell + kRowTile - 1) / kRowTile;
+    if (producer)
+        stage_tile(tile[0], tid, 0, (int)(n_cell < kRowTile ? n_cell : kRowTile), g0, blockIdx.x, n_cell, indptr,
+                   indices, data, tptr);
+    __syncthreads();
+    for (int64_t rt = 0; rt < n_rt; ++rt) {
+        const int64_t r0 = rt * kRowTile;
         const int nr = (int)((n_cell - r0) < kRowTile ? (n_cell - r0) : kRowTile);
-        __syncthreads();
-        for (int i = threadIdx.x; i < kRowTile * (kGeneTile + 1); i += kGeneTile) (&tile[0][0])[i] = 0.f;
-        __syncthreads();
-        if ((int)threadIdx.x < nr) {
-            const int64_t p0 = indptr[r0 + threadIdx.x], p1 = indptr[r0 + threadIdx.x + 1];
-            int64_t lo = p0, hi = p1;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (indices[mid] < g0) lo = mid + 1; else hi = mid;
+        if (producer) {
+            if (rt + 1 < n_rt) {
+                const int64_t r1 = r0 + kRowTile;
+                stage_tile(tile[(rt + 1) & 1], tid, r1, (int)((n_cell - r1) < kRowTile ? (n_cell - r1) : kRowTile), g0,
+                           blockIdx.x, n_cell, indptr, indices, data, tptr);
             }
-            for (int64_t t = lo; t < p1; ++t) {
-                const int col = indices[t] - g0;
-                if (col >= kGeneTile) break;
-                tile[threadIdx.x][col] = data[t];
-            }
-        }
-        __syncthreads();
-        if (ok) {
+        } else if (ok) {
+            float (*cur)[kGeneTile + 1] = tile[rt & 1];
             for (int r = 0; r < nr; ++r) {
-                const float x = tile[r][threadIdx.x];
+                const float x = cur[r][tid];
                 if (x != 0.f) {      // only stored entries take part, as in the sparse products
                     s32 = __fadd_rn(s32, __fmul_rn(x, inv_n));
                     const double xd = (double)x;
@@ -169,6 +279,7 @@ gene_mean_xtc_kernel(int64_t n_cell, int n_gene, int k, float inv_n,
                 }
             }
         }
+        __syncthreads();
     }
     if (ok) {
         gmean32[g] = s32;
@@ -181,10 +292,11 @@ gene_mean_xtc_kernel(int64_t n_cell, int n_gene, int k, float inv_n,
 int gene_mean_xtc(scdrs_ctx* c, int k, const double* dev_cov, float* dev_gmean32, double* dev_xtc) {
     SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set (call scdrs_set_csr_* first)");
     SCDRS_CHECK(k >= 0 && k <= kMaxCovReg, "this kernel handles at most %d covariates (got %d)", kMaxCovReg, k);
+    SCDRS_TRY(ensure_tile_ptr(c));
     const int tiles = (c->n_gene + kGeneTile - 1) / kGeneTile;
-    gene_mean_xtc_kernel<<<tiles, kGeneTile, 0, c->stream>>>(
-        c->n_cell, c->n_gene, k, (float)(1.0 / (double)c->n_cell), c->indptr, c->indices, c->data, dev_cov,
-        dev_gmean32, dev_xtc);
+    gene_mean_xtc_kernel<<<tiles, kStatThreadsSeq, 0, c->stream>>>(
+        c->n_cell, c->n_gene, k, (float)(1.0 / (double)c->n_cell), c->indptr, c->indices, c->data,
+        c->tile_ptr_valid ? c->tile_ptr.as<uint32_t>() : nullptr, dev_cov, dev_gmean32, dev_xtc);
     SCDRS_LAUNCH_CHECK(c);
     return 0;
 }
@@ -261,12 +373,14 @@ static int run_stats(scdrs_ctx* c, const double* dev_cell_w, int center, double 
     const int64_t n_cell = c->n_cell;
     if (gsum != nullptr) {
         const int tiles = (n_gene + kGeneTile - 1) / kGeneTile;
-        const size_t smem = (size_t)(k > 0 ? k : 1) * kGeneTile * sizeof(double);
+        const size_t smem = (size_t)((k > 0 ? k : 1) + 1) * kGeneTile * sizeof(double);
         SCDRS_CHECK(smem <= 150 * 1024, "too many covariates (%d) for the statistics kernel", k);
         SCDRS_CUDA(cudaFuncSetAttribute(stats_gene_seq_kernel<TRANSFORM>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-        stats_gene_seq_kernel<TRANSFORM><<<tiles, kGeneTile, smem, c->stream>>>(
-            n_cell, n_gene, k, center, denom, c->indptr, c->indices, c->data, c->cov_mat.as<double>(),
+        SCDRS_TRY(ensure_tile_ptr(c));
+        stats_gene_seq_kernel<TRANSFORM><<<tiles, kSeqThreads, smem, c->stream>>>(
+            n_cell, n_gene, k, center, denom, c->indptr, c->indices, c->data,
+            c->tile_ptr_valid ? c->tile_ptr.as<uint32_t>() : nullptr, c->cov_mat.as<double>(),
             c->cov_beta.as<double>(), c->gene_mean.as<double>(), dev_cell_w, gsum, gsq);
         SCDRS_LAUNCH_CHECK(c);
     }
