@@ -128,3 +128,34 @@ class ShardedScorer:
         out = self.p.finish(hist, self.n_total, self.offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm)
         out["n_null_total"] = n_null_total
         return out
+
+
+def broadcast_prep(prep, src, n_ctrl, n_s_max, device):
+    """Ship one trait's host-drawn gene sets (``method._prepare_trait``) from rank ``src`` to all ranks.
+
+    One int32 buffer over NCCL: [n_s, n_sc, trait_cols, ctrl_cols, trait_gw (f64 bits), ctrl_gw (f64 bits)],
+    sized for the largest possible trait (n_s_max genes) so that receivers need no size exchange."""
+    cap = 2 + n_s_max + n_ctrl * n_s_max + 4 * n_s_max
+    if prep is not None:
+        n_s, n_sc = int(prep["trait_cols"].shape[0]), int(prep["ctrl_cols"].shape[1])
+        host = np.empty(cap, dtype=np.int32)
+        host[0], host[1] = n_s, n_sc
+        o = 2
+        host[o:o + n_s] = prep["trait_cols"]; o += n_s
+        host[o:o + n_ctrl * n_sc] = np.ascontiguousarray(prep["ctrl_cols"], dtype=np.int32).reshape(-1); o += n_ctrl * n_sc
+        host[o:o + 2 * n_s] = np.ascontiguousarray(prep["trait_gw"], dtype=np.float64).view(np.int32); o += 2 * n_s
+        host[o:o + 2 * n_sc] = np.ascontiguousarray(prep["ctrl_gw"], dtype=np.float64).view(np.int32)
+        buf = torch.from_numpy(host).to(device)
+    else:
+        buf = torch.empty(cap, dtype=torch.int32, device=device)
+    dist.broadcast(buf, src=src)
+    if prep is not None:
+        return prep
+    host = buf.cpu().numpy()
+    n_s, n_sc = int(host[0]), int(host[1])
+    o = 2
+    trait_cols = host[o:o + n_s].copy(); o += n_s
+    ctrl_cols = host[o:o + n_ctrl * n_sc].reshape(n_ctrl, n_sc).copy(); o += n_ctrl * n_sc
+    trait_gw = host[o:o + 2 * n_s].copy().view(np.float64); o += 2 * n_s
+    ctrl_gw = host[o:o + 2 * n_sc].copy().view(np.float64)
+    return dict(trait_cols=trait_cols, trait_gw=trait_gw, ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw)

@@ -399,8 +399,20 @@ def score_traits(
     results = {}
     with ThreadPoolExecutor(max_workers=n_jobs) as pool, ThreadPoolExecutor(max_workers=2) as frame_pool:
         # the control draws of every trait start now; the upload of X overlaps with the first of them
+        world, rank = 1, 0
+        if sharded:
+            import torch
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                world, rank = dist.get_world_size(), dist.get_rank()
+        # Every rank needs the same control sets; the draws (~0.2 s of one core per trait) are dealt
+        # round-robin over the ranks and broadcast, instead of every rank drawing all of them.
+        share_draws = world > 1 and os.environ.get("SCDRS_B200_LOCAL_DRAWS", "0") != "1"
         futs = {}
-        for t in traits:
+        for i_t, t in enumerate(traits):
+            if share_draws and i_t % world != rank:
+                continue
             g, w = dict_gs[t]
             futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
                                   tab, bins)
@@ -408,9 +420,7 @@ def score_traits(
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
         if sharded:
-            import torch
-
-            from .distributed import CudaPhases, ShardedScorer
+            from .distributed import CudaPhases, ShardedScorer, broadcast_prep
 
             dev = torch.device("cuda", torch.cuda.current_device())
             scorer = ShardedScorer(CudaPhases(ctx, dev), dev)
@@ -428,8 +438,13 @@ def score_traits(
                 else:
                     on_result(t_done, df_done)
 
-        for t in traits:
-            prep = futs.pop(t).result()
+        for i_t, t in enumerate(traits):
+            if share_draws:
+                owner = i_t % world
+                prep = broadcast_prep(futs.pop(t).result() if owner == rank else None, owner, n_ctrl,
+                                      len(dict_gs[t][0]), dev)
+            else:
+                prep = futs.pop(t).result()
             out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
                             weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
                             want_ctrl_norm=return_ctrl_norm_score)

@@ -147,3 +147,34 @@ def test_sharded_scoring_equals_unsharded(tmp_path, world):
     assert np.array_equal(full["mc_count"], info["mc_count"])
     d = np.abs(full["ge_count"] - info["ge_count"])
     assert d.max() <= 2 and (d > 0).mean() < 0.02
+
+
+def _run_bcast(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scdrs_b200.distributed import broadcast_prep
+
+        n_ctrl, n_s_max = 7, 40
+        for src in range(world):                      # every rank owns a trait in turn, ragged sizes
+            rng = np.random.default_rng(100 + src)
+            n_s, n_sc = 33 - src, 31 - src            # some trait genes fell in no bin: n_sc < n_s
+            mine = dict(trait_cols=rng.integers(0, 5000, n_s).astype(np.int32),
+                        trait_gw=rng.random(n_s), ctrl_gw=rng.random(n_sc),
+                        ctrl_cols=rng.integers(0, 5000, (n_ctrl, n_sc)).astype(np.int32))
+            got = broadcast_prep(mine if rank == src else None, src, n_ctrl, n_s_max, torch.device("cpu"))
+            for k, v in mine.items():                 # same generator on every rank: `mine` is the truth
+                assert got[k].dtype == v.dtype and np.array_equal(got[k], v), (rank, src, k)
+        open(os.path.join(out_dir, "bcast_ok_%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_control_sets_drawn_by_one_rank_reach_all_ranks(tmp_path):
+    """score_traits(sharded=True) deals the control-set draws over the ranks and broadcasts them."""
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_run_bcast, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "bcast_ok_%d" % r)) for r in range(2))
