@@ -429,6 +429,38 @@ def main():
                 ("bound by the shared-memory/L1 data pipe (89% busy in ncu: one 64-bit load+store per accumulate, "
                  "1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4")}
 
+    # ---- per-phase device times of one trait (CUDA events between the C-ABI phases), single GPU only
+    phases = None
+    if world == 1:
+        ncol = 1 + n_ctrl
+        t_cs = torch.empty(ncol, dtype=torch.float64, device=device)
+        t_c2, t_cm = torch.empty_like(t_cs), torch.empty_like(t_cs)
+        t_q = torch.empty(n_cell, dtype=torch.float32, device=device)
+        t_h = torch.empty(n_cell + 1, dtype=torch.int64, device=device)
+        acc = np.zeros(6)
+        reps = preps[: min(3, len(preps))]
+        for p in reps:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
+            ctx.trait_raw(p["trait_cols"], p["trait_gw"], p["ctrl_cols"], p["ctrl_gw"], "vs", True, t_cs.data_ptr()); ev[1].record()
+            ctx.trait_rowstats(t_cs.data_ptr(), n_cell, t_c2.data_ptr(), t_cm.data_ptr()); ev[2].record()
+            ctx.trait_queries(t_c2.data_ptr(), t_cm.data_ptr(), t_q.data_ptr()); ev[3].record()
+            ctx.trait_count(t_q.data_ptr(), n_cell, t_h.data_ptr()); ev[4].record()
+            ctx.trait_finish(t_h.data_ptr(), n_cell, 0, n_cell * n_ctrl, n_ctrl); ev[5].record()
+            torch.cuda.synchronize()
+            acc[:5] += [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
+            acc[5] += ctx.last_timing()[0]
+        acc /= len(reps)
+        mat_bytes = 4.0 * n_cell * (1 + n_ctrl)
+        phases = {
+            "raw_ms": acc[0], "scatter_ms": acc[5], "raw_other_ms": acc[0] - acc[5], "rowstats_ms": acc[1],
+            "queries_ms": acc[2], "count_ms": acc[3], "finish_ms": acc[4],
+            "note": "raw_other = set upload + gene-major lists + matching + column sums; count = sort of the queries + "
+                    "grid + one pass over the null; finish = suffix sums + result download",
+            "rowstats_GBps_of_one_read": mat_bytes / (acc[1] * 1e-3) / 1e9,
+            "count_GBps_of_one_read": mat_bytes / (acc[3] * 1e-3) / 1e9,
+        }
+
     # ---- end to end through the public API with host inputs
     e2e = None
     if not args.no_e2e:
@@ -472,7 +504,7 @@ def main():
             "vs_baseline": None, "dtype": "s32 fixed point (exact sums) + f64" if spmm_kind == "fixed" else "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "setup": info,
+            "roofline": roofline, "cpu_baseline": cpu, "phases": phases, "setup": info,
             "device_ms_per_trait": 1e3 * wall / args.steps / len(names), "wall_s_check": wall_check,
         }
         print(json.dumps(line))

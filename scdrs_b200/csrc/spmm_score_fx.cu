@@ -33,7 +33,7 @@ constexpr int kFxItemOff = kFxTrashOff + 128;   // byte offset of the staged wor
 constexpr int kFxItemCap = 128;                 // four passes over a chunk of 32 stored entries
 constexpr int kFxMaxDepth = 8;                  // register slots of the item pipeline
 constexpr int kFxWarpsPerBlock = 10, kFxBlocksPerSM = 2;   // 20 warps per SM at <= 96 registers
-constexpr int kFxWarpBytes = kFxItemOff + (kFxItemCap + kFxMaxDepth) * 8;
+constexpr int kFxWarpBytes = kFxItemOff + (kFxItemCap + 2 * kFxMaxDepth) * 8;
 constexpr int kFxItemBits = 25;               // |item| <= 2^25: 32 stored entries add at most 2^30
 constexpr uint32_t kFxFlushAt = 0x7f000000u;  // flush before the bound on any word reaches this
 constexpr uint32_t kFxInflight = ((uint32_t)kFxMaxDepth << kFxItemBits) + 64u;   // bound on the items held in the register slots
@@ -448,6 +448,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
         };
 
         uint32_t lbound = 0;
+        uint32_t n_left = 0;          // staged items not yet in the slots (fewer than D), carried to the next group
         const int64_t p0 = indptr[row], p1 = indptr[row + 1];
         // chunk pipeline registers: record + value of the current chunk, ids + values of the next two
         int4 gi0 = make_int4(0, 0, 0, 0);
@@ -462,7 +463,23 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
         for (int64_t base = p0;; base += 32) {
             const bool done = base >= p1;
             if (done) {
-                // drain the slots before the last flush
+                // drain the slots, then the staged left-overs through the slots, before the last flush
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < D; ++u) apply(u);
+#pragma unroll
+                for (int u = 0; u < D; ++u) {
+                    if ((uint32_t)u < n_left) {                         // warp-uniform
+                        const uint2 it = items[u];
+                        const uint32_t t = it.x * 32u + lane;
+                        s_ids[u] = __ldg(p_col32 + t);
+                        if (WEIGHTED) s_w[u] = __ldg(p_val2 + t);
+                        s_x[u] = (int)it.y;
+                    } else {
+                        s_ids[u] = trash_ids;
+                        s_x[u] = 0;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < D; ++u) apply(u);
             }
@@ -496,7 +513,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                         hi[t] += (a >> 12) + (b >> 12);
                     }
                 }
-                lbound = kFxInflight / 32u + 4096u / 32u + 1u;   // slot items land after the flush; words keep 12 bits
+                lbound = 2u * kFxInflight / 32u + 4096u / 32u + 1u;   // slot and staged items land after the flush; words keep 12 bits
             }
             if (done) break;
             lbound += qb;
@@ -513,7 +530,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                 uint32_t m = __ballot_sync(0xffffffffu, nblk > pg);
                 if (m == 0u) break;
                 __syncwarp();
-                uint32_t n_items = 0;
+                uint32_t n_items = n_left;
 #pragma unroll
                 for (uint32_t dp = 0; dp < 4; ++dp) {
                     const uint32_t pass = pg + dp;
@@ -521,7 +538,9 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                     if (nblk > pass) items[n_items + __popc(m & lt_mask)] = make_uint2(blk0 + pass, (uint32_t)xq);
                     n_items += __popc(m);
                 }
-                if (lane < D) items[n_items + lane] = make_uint2(0u, 0u);   // bubbles
+                // whole rounds of D now; the remainder waits (no bubbles inside a row)
+                n_left = n_items % (uint32_t)D;
+                n_items -= n_left;
                 __syncwarp();
 #pragma unroll 1
                 for (uint32_t i = 0; i < n_items; i += D) {
@@ -536,6 +555,12 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                         if (WEIGHTED) s_w[u] = __ldg(p_val2 + t);
                         s_x[u] = (int)it.y;
                     }
+                }
+                if (n_left != 0u && n_items != 0u) {                     // warp-uniform
+                    uint2 keep = make_uint2(0u, 0u);
+                    if (lane < n_left) keep = items[n_items + lane];
+                    __syncwarp();
+                    if (lane < n_left) items[lane] = keep;
                 }
             }
             gi0 = gi1;
