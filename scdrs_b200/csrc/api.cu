@@ -68,7 +68,8 @@ static void release_all(scdrs_ctx* c) {
                       &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
-                      &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr};
+                      &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
+                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -228,6 +229,9 @@ int scdrs_set_csr_host(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64
     c->have_stats = false;
     c->fx_stat_key = -1;
     c->tile_ptr_valid = false;
+    c->xsum_valid = false;
+    c->covsum_valid = false;
+    c->colsum_ready = false;
     c->k = 0;
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -251,6 +255,9 @@ int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_
     c->have_stats = false;
     c->fx_stat_key = -1;
     c->tile_ptr_valid = false;
+    c->xsum_valid = false;
+    c->covsum_valid = false;
+    c->colsum_ready = false;
     c->k = 0;
     return 0;
 }
@@ -281,6 +288,8 @@ int scdrs_set_cov(scdrs_ctx* c, int32_t k, const double* cov_mat, const double* 
     }
     c->k = k;
     c->trait_ready = false;
+    c->covsum_valid = false;
+    c->colsum_ready = false;
     return 0;
 }
 

@@ -102,6 +102,12 @@ static int grid_for(int64_t n_cell) {
 
 int bg_colsum(scdrs_ctx* c, double* dev_colsum_out) {
     SCDRS_CHECK(c->trait_ready, "no raw scores resident (call scdrs_trait_raw first)");
+    if (c->colsum_ready) {
+        // already known by algebra from the per-gene sums of X (prep_sets_kernel): no pass over the matrix
+        SCDRS_CUDA(cudaMemcpyAsync(dev_colsum_out, c->colsum_alg.p, (size_t)c->ncol * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
     const int g = grid_for(c->n_cell);
     SCDRS_TRY(c->partial.reserve((size_t)g * c->ncol * sizeof(double) * 2));
     SCDRS_CHECK((size_t)c->ncol * 8 <= 160 * 1024, "1 + n_ctrl too large");

@@ -65,6 +65,9 @@ struct scdrs_ctx {
     scdrs::DevBuf own_indptr, own_indices, own_data;
     scdrs::DevBuf tile_ptr;        // where every gene tile starts inside every CSR row (stats.cu)
     bool tile_ptr_valid = false;
+    // column sums of the raw scores by algebra: sum_c raw[c, j] = (sum_c X[c, :]) . w_j + covariate terms
+    scdrs::DevBuf gene_xsum, cov_colsum, colsum_alg, fx_scal;
+    bool xsum_valid = false, covsum_valid = false, colsum_ready = false;
 
     // gene-level vectors
     scdrs::DevBuf var, var_tech;

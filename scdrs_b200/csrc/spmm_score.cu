@@ -67,7 +67,9 @@ __global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int binary
                                  const double* __restrict__ beta, const double* __restrict__ gmean,
                                  float* __restrict__ set_val, double* __restrict__ colscale,
                                  double* __restrict__ covM, double* __restrict__ covm,
-                                 double* __restrict__ rnum) {
+                                 double* __restrict__ rnum, const double* __restrict__ xsum,
+                                 const double* __restrict__ cov_colsum, double n_cell_d,
+                                 double* __restrict__ colsum_alg) {
     __shared__ double sh[32];
     const int j = blockIdx.x;
     const int n_s = j == 0 ? n_s0 : n_sc;
@@ -83,7 +85,7 @@ __global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int binary
     }
     // binary sets scatter the constant 1 and fold the common gene weight into the column scale
     const double cs = binary ? (n_s > 0 ? g[0] : 1.0) / s : 1.0 / s;
-    double pm = 0.0, pr = 0.0;
+    double pm = 0.0, pr = 0.0, px = 0.0;
     for (int p = threadIdx.x; p < n_s; p += blockDim.x) {
         const int gi = genes[p];
         const double w = gbase[gi] * g[p] / s;                          // the reference's weight
@@ -92,21 +94,74 @@ __global__ void prep_sets_kernel(int n_s0, int n_sc, int ncol, int k, int binary
         const double wf = (double)val * gbase[gi] * cs;                 // the weight actually applied
         if (k > 0) pm += gmean[gi] * wf;
         if (var != nullptr) pr += var[gi] * w * w;
+        if (xsum != nullptr) px += xsum[gi] * wf;
     }
     pm = block_sum(pm, sh);
     pr = block_sum(pr, sh);
+    px = block_sum(px, sh);
     if (threadIdx.x == 0) {
         covm[j] = pm;
         rnum[j] = pr;
         colscale[j] = cs;
     }
+    // column sum of the raw scores of this set over all cells, without touching the score matrix:
+    // sum_c raw[c, j] = (sum_c X[c, :]) . w_j + (sum_c C[c, :]) . M[:, j] + n_cell m[j]
+    double total = px + n_cell_d * pm;
     for (int kk = 0; kk < k; ++kk) {
         double pb = 0.0;
         for (int p = threadIdx.x; p < n_s; p += blockDim.x)
             pb += beta[(size_t)genes[p] * k + kk] * ((double)vout[p] * gbase[genes[p]] * cs);
         pb = block_sum(pb, sh);
         if (threadIdx.x == 0) covM[(size_t)kk * ncol + j] = pb;
+        if (cov_colsum != nullptr) total += cov_colsum[kk] * pb;
     }
+    if (threadIdx.x == 0 && colsum_alg != nullptr) colsum_alg[j] = total;
+}
+
+// ---- per-matrix sums behind the algebraic column sums -------------------------------------------------
+// sum_c X[c, g] in 2^-24 fixed point (integer atomics: exact and independent of the order)
+__global__ void __launch_bounds__(256)
+xsum_kernel(int64_t nnz, const int32_t* __restrict__ indices, const float* __restrict__ data,
+            unsigned long long* __restrict__ acc) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&acc[indices[q]], (unsigned long long)__double2ll_rn((double)data[q] * 16777216.0));
+}
+__global__ void xsum_finish_kernel(int n_gene, const unsigned long long* __restrict__ acc, double* __restrict__ xsum) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_gene) xsum[g] = (double)(long long)acc[g] * (1.0 / 16777216.0);
+}
+// sum_c COV_MAT[c, kk], one block per covariate, fixed order
+__global__ void __launch_bounds__(256)
+cov_colsum_kernel(int64_t n_cell, int k, const double* __restrict__ cov_mat, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const int kk = blockIdx.x;
+    double part = 0.0;
+    for (int64_t r = threadIdx.x; r < n_cell; r += blockDim.x) part += cov_mat[r * k + kk];
+    part = block_sum(part, sh);
+    if (threadIdx.x == 0) out[kk] = part;
+}
+
+static int ensure_matrix_sums(scdrs_ctx* c) {
+    if (!c->xsum_valid) {
+        SCDRS_TRY(c->gene_xsum.reserve((size_t)c->n_gene * sizeof(double)));
+        SCDRS_TRY(c->stage.reserve((size_t)c->n_gene * sizeof(unsigned long long)));
+        SCDRS_CUDA(cudaMemsetAsync(c->stage.p, 0, (size_t)c->n_gene * sizeof(unsigned long long), c->stream));
+        if (c->nnz > 0) {
+            xsum_kernel<<<kNumSM * 8, 256, 0, c->stream>>>(c->nnz, c->indices, c->data, c->stage.as<unsigned long long>());
+            SCDRS_LAUNCH_CHECK(c);
+        }
+        xsum_finish_kernel<<<(c->n_gene + 255) / 256, 256, 0, c->stream>>>(c->n_gene, c->stage.as<unsigned long long>(),
+                                                                          c->gene_xsum.as<double>());
+        SCDRS_LAUNCH_CHECK(c);
+        c->xsum_valid = true;
+    }
+    if (c->k > 0 && !c->covsum_valid) {
+        SCDRS_TRY(c->cov_colsum.reserve((size_t)c->k * sizeof(double)));
+        cov_colsum_kernel<<<c->k, 256, 0, c->stream>>>(c->n_cell, c->k, c->cov_mat.as<double>(), c->cov_colsum.as<double>());
+        SCDRS_LAUNCH_CHECK(c);
+        c->covsum_valid = true;
+    }
+    return 0;
 }
 
 // 1/sqrt(var ratio) per column; column 0 (the trait) and the no-ratio case get 1.
@@ -362,6 +417,11 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_TRY(c->w_val.reserve(n_entry * sizeof(float)));
     c->w_binary = binary;
     c->w_fx = false;
+    c->colsum_ready = false;
+    if (!explicit_w) {
+        SCDRS_TRY(ensure_matrix_sums(c));
+        SCDRS_TRY(c->colsum_alg.reserve(ncol * sizeof(double)));
+    }
 
     gene_base_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(
         n_gene, explicit_w ? SCDRS_WEIGHT_UNIFORM : weight_opt,
@@ -374,8 +434,11 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
         explicit_w ? c->stage.as<double>() : nullptr, c->gbase.as<double>(),
         c->have_stats ? c->var.as<double>() : nullptr, c->cov_beta.as<double>(),
         c->gene_mean.as<double>(), c->set_w.as<float>(), c->colscale.as<double>(),
-        c->covM.as<double>(), c->covm.as<double>(), rnum);
+        c->covM.as<double>(), c->covm.as<double>(), rnum, explicit_w ? nullptr : c->gene_xsum.as<double>(),
+        (!explicit_w && c->k > 0) ? c->cov_colsum.as<double>() : nullptr, (double)c->n_cell,
+        explicit_w ? nullptr : c->colsum_alg.as<double>());
     SCDRS_LAUNCH_CHECK(c);
+    c->colsum_ready = !explicit_w;
     ratio_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(ncol, use_var_ratio, rnum,
                                                             c->ratio_a.as<double>());
     SCDRS_LAUNCH_CHECK(c);

@@ -307,6 +307,29 @@ __global__ void fx_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, c
     }
 }
 
+// Column means of the per-set constants: what the scatter kernel needs to place a cell's reference value
+// (an estimate of its mean raw score) without a pass over the per-column constants.
+// out[0] = mean colscale, out[1] = mean covm, out[2 + kk] = mean covM[kk, :].  One block, fixed order.
+__global__ void __launch_bounds__(256)
+fx_scalars_kernel(int ncol, int k, const double* __restrict__ colscale, const double* __restrict__ covm,
+                  const double* __restrict__ covM, double* __restrict__ out) {
+    __shared__ double sh[256];
+    for (int q = 0; q < 2 + k; ++q) {
+        const double* src = q == 0 ? colscale : (q == 1 ? covm : covM + (size_t)(q - 2) * ncol);
+        double part = 0.0;
+        if (q != 1 || k > 0)
+            for (int j = threadIdx.x; j < ncol; j += 256) part += src[j];
+        sh[threadIdx.x] = part;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[q] = sh[0] / (double)ncol;
+        __syncthreads();
+    }
+}
+
 // Called by build_w after the compact gene-major lists (w_ptr, w_col, w_val) exist.
 int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax) {
     const int n_gene = c->n_gene;
@@ -343,6 +366,10 @@ int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax) {
     SCDRS_LAUNCH_CHECK(c);
     fx_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(), c->w_rounds.as<uint32_t>(),
                                                                c->gbase.as<double>(), ldexp(1.0, shift), c->p_meta.as<GeneInfo>());
+    SCDRS_LAUNCH_CHECK(c);
+    SCDRS_TRY(c->fx_scal.reserve((size_t)(2 + (c->k > 0 ? c->k : 0)) * sizeof(double)));
+    fx_scalars_kernel<<<1, 256, 0, c->stream>>>(c->ncol, c->k, c->colscale.as<double>(), c->covm.as<double>(),
+                                                 c->covM.as<double>(), c->fx_scal.as<double>());
     SCDRS_LAUNCH_CHECK(c);
     c->w_fx = true;
     return 0;
@@ -413,7 +440,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                      const float2* __restrict__ p_val2, const double* __restrict__ colscale,
                      double inv_scale, float gwmax, int k, const double* __restrict__ cov_mat,
                      const double* __restrict__ covM, const double* __restrict__ covm,
-                     float* __restrict__ dev_mat, double* __restrict__ row_ref) {
+                     const double* __restrict__ scal, float* __restrict__ dev_mat, double* __restrict__ row_ref) {
     static_assert(D <= kFxMaxDepth && (kFxItemCap % D) == 0, "pipeline depth");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -579,38 +606,43 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                 accw[ib] = (uint32_t)(lo & 0xfff);
             }
         }
-        // epilogue: column scale, covariate terms, row reference, deviations; two passes, the values
-        // are recomputed bit for bit instead of being held in 64 registers
-        auto column_value = [&](int t, int j) -> double {
-            const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
-            const long long total = ((long long)(int)accw[ia] << 12) + (long long)accw[ib];
-            double v = ((double)total * inv_scale) * colscale[j];
-            if (k > 0) {
-                double cterm = covm[j];
-                for (int kk = 0; kk < k; ++kk)
-                    cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
-                v += cterm;
-            }
-            return v;
-        };
-        double rs = 0.0;
+        // epilogue: row reference, then column scale, covariate terms and deviations in one pass.
+        // The reference only has to lie near the cell's mean raw score (consumers use ref + deviation):
+        // it is estimated from the integer totals and the column means of the per-set constants, which
+        // saves a second pass over those constants.
+        long long isum = 0;
 #pragma unroll 1
         for (int t = 0; t * 32 < ncol; ++t) {
             const int j = t * 32 + lane;
-            if (j < ncol) rs += column_value(t, j);
+            if (j < ncol)
+                isum += ((long long)(int)accw[t * 32 + lane] << 12) + (long long)accw[kFxNB + t * 32 + ((lane + t) & 31)];
         }
-        rs = fx_warp_sum(rs);
-        const double ref = rs / (double)ncol;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+        double ref = ((double)isum * inv_scale) * scal[0] / (double)ncol;
+        if (k > 0) {
+            double cterm = scal[1];
+            for (int kk = 0; kk < k; ++kk) cterm = fma(cov_mat[row * k + kk], scal[2 + kk], cterm);
+            ref += cterm;
+        }
         float* out = dev_mat + row * (int64_t)ld;
 #pragma unroll 1
         for (int t = 0; t * 32 < ncol; ++t) {
             const int j = t * 32 + lane;
+            const int ia = t * 32 + lane, ib = kFxNB + t * 32 + ((lane + t) & 31);
             if (j < ncol) {
-                const double v = column_value(t, j);
+                const long long total = ((long long)(int)accw[ia] << 12) + (long long)accw[ib];
+                double v = ((double)total * inv_scale) * colscale[j];
+                if (k > 0) {
+                    double cterm = covm[j];
+                    for (int kk = 0; kk < k; ++kk)
+                        cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
+                    v += cterm;
+                }
                 out[j] = (v == 0.0) ? __int_as_float(0x7fc00000) : (float)(v - ref);
             }
-            accw[t * 32 + lane] = 0u;
-            accw[kFxNB + t * 32 + ((lane + t) & 31)] = 0u;
+            accw[ia] = 0u;
+            accw[ib] = 0u;
         }
         if (lane == 0) row_ref[row] = ref;
     }
@@ -641,14 +673,14 @@ int fx_spmm(scdrs_ctx* c) {
         spmm_score_fx_kernel<false, kFxDepthBinary><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
             c->n_cell, ncol, c->ld, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
             c->p_col.as<uint32_t>(), nullptr, c->colscale.as<double>(), inv_scale, c->fx_gwmax, c->k,
-            c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->dev_mat.as<float>(),
-            c->row_ref.as<double>());
+            c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->fx_scal.as<double>(),
+            c->dev_mat.as<float>(), c->row_ref.as<double>());
     else
         spmm_score_fx_kernel<true, kFxDepthWeighted><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
             c->n_cell, ncol, c->ld, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
             c->p_col.as<uint32_t>(), c->p_val.as<float2>(), c->colscale.as<double>(), inv_scale, c->fx_gwmax,
-            c->k, c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->dev_mat.as<float>(),
-            c->row_ref.as<double>());
+            c->k, c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->fx_scal.as<double>(),
+            c->dev_mat.as<float>(), c->row_ref.as<double>());
     SCDRS_LAUNCH_CHECK(c);
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->trait_ready = true;
