@@ -411,23 +411,37 @@ def main():
     alg_bytes = 8 * nnz + 8 * (n_cell + 1) + 4 * k * n_cell + 4 * n_cell * (1 + n_ctrl)
     k1_ms = float(np.mean(spmm_ms)) if spmm_ms else float("nan")
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, binding = None, None
     tpath = os.path.join(ROOT, "profiles", "r1_spmm_traffic.json")
     if os.path.exists(tpath) and (args.n_cell, args.n_gene, args.n_ctrl) == (110096, 20000, 1000):
-        traffic = float(json.load(open(tpath))["dram_bytes_total"])   # from the committed ncu capture
+        prof = json.load(open(tpath))
+        traffic = float(prof["dram_bytes_total"])   # from the committed ncu capture
+        if "lsu_data_pipe_pct_of_peak" in prof:
+            # the resource that actually binds the scatter: the SM's LSU data pipe takes one wavefront per
+            # clock; floor = wavefronts of the ncu capture / (SMs x clock), against the live launch time
+            wf = float(prof["lsu_data_pipe_pct_of_peak"]) / 100.0 * 9.227e-3 * 1.965e9 * 148
+            floor_ms = wf / (148 * 1.965e9) * 1e3
+            binding = {"resource": "LSU data pipe (shared-memory + L1 wavefronts, one per SM per clock)",
+                       "wavefronts_per_launch": wf, "floor_ms": floor_ms,
+                       "frac_of_floor": None, "source": "profiles/r1_spmm_fx_ncu_summary.md"}
     spmm_kind, spmm_shift = ctx.last_spmm_kind()
     roofline = {"bound": "hbm", "kernel": "spmm_score_fx_kernel" if spmm_kind == "fixed" else "spmm_score_kernel",
                 "arithmetic": ("exact integer sums of round(x*base*2^%d), 32-bit shared-memory words, 64-bit totals" % spmm_shift)
                 if spmm_kind == "fixed" else "fp64 accumulators in shared memory",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_ms, "binding_resource": binding,
                 "scatter_fma_per_launch": float(nnz) * (1 + n_ctrl) * args.n_trait_gene / args.n_gene,
                 "note": ("bound by the LSU / shared-memory data pipe (86% busy in ncu: one conflict-free 32-bit load + "
                          "store per accumulate, 1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4")
                 if spmm_kind == "fixed" else
                 ("bound by the shared-memory/L1 data pipe (89% busy in ncu: one 64-bit load+store per accumulate, "
                  "1.1e10 accumulates per launch), not by HBM; see DESIGN.md section 4")}
+
+    if binding is not None and spmm_kind == "fixed" and not getattr(args, "weighted", False):
+        binding["frac_of_floor"] = binding["floor_ms"] / k1_ms
+    else:
+        roofline["binding_resource"] = None
 
     # ---- per-phase device times of one trait (CUDA events between the C-ABI phases), single GPU only
     phases = None
