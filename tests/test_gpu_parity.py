@@ -599,3 +599,23 @@ def test_score_traits_equal_score_cell(native_lib):
     bad["broken"] = (["not_a_gene"], [1.0])
     with pytest.raises(Exception):
         scdrs_b200.score_traits(adata, bad, n_ctrl=20)
+
+
+def test_categorical_custom_match_key(sc):
+    """A custom match key with few levels takes the reference's categorical branch (groupby instead of
+    qcut, scdrs/method.py:284-285); no variance ratio then (:186-195)."""
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(500, 1200, density=0.15, seed=61)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    gs = adata.uns["SCDRS_PARAM"]["GENE_STATS"]
+    gs["mykey"] = pd.qcut(gs["mean"], 12, labels=False, duplicates="drop").astype(float)
+    genes, w = synth.make_traits(adata.var_names, 1, 150, weighted=True, seed=13)["trait_00"]
+    for n_ctrl in (37, 1000):
+        ref = orc.score_cell(adata, genes, gene_weight=w, ctrl_match_key="mykey", n_ctrl=n_ctrl,
+                             return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+        df = sc.score_cell(adata, genes, gene_weight=w, ctrl_match_key="mykey", n_ctrl=n_ctrl,
+                           return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+        _check_counts_self_consistent(df, n_ctrl)
+        _compare_with_reference(df, ref, n_ctrl, adata.shape[0])
