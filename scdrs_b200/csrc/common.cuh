@@ -86,6 +86,8 @@ struct scdrs_ctx {
     int spmm_mode = 0;        // 0 auto, 1 fp64 accumulators, 2 fixed point (error if not applicable)
     bool w_fx = false;        // the lists currently built are laid out for the fixed-point kernel
     int fx_shift = 0;         // scale = 2^fx_shift
+    int fx_n_tile = 1;        // column tiles of the fixed-point scatter
+    bool fx_tile0_built = false;
     int fx_stat_key = -1;     // weight_opt the value statistics below were computed for (-1: none)
     double fx_vmax = 0.0, fx_vmean = 0.0;   // max and mean of |x * base_g| over the stored entries
     float fx_gwmax = 1.f;
@@ -127,11 +129,13 @@ struct __align__(16) GeneInfo {
 };
 
 // ---- spmm_score_fx.cu ---------------------------------------------------------------------
-constexpr int kFxMaxCol = 1024;   // the fixed-point kernel keeps one 64-bit total per column and lane in registers
+constexpr int kFxMaxCol = 1024;   // columns per pass: the fixed-point kernel keeps one total per column and lane in registers
+constexpr int kFxMaxTiles = 32;   // wider score matrices are scattered in column tiles of kFxMaxCol sets, one pass over X each
 bool fx_applicable(scdrs_ctx* c, int ncol, bool explicit_w);
 int fx_value_stats(scdrs_ctx* c, int weight_opt);
-int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax);
+int fx_prepare(scdrs_ctx* c, bool binary, double gw_absmax);
 int fx_spmm(scdrs_ctx* c);
+int build_gene_lists(scdrs_ctx* c, int col0, int col1);   // spmm_score.cu
 
 // ---- background.cu ------------------------------------------------------------------------
 int bg_colsum(scdrs_ctx* c, double* dev_colsum_out);

@@ -175,9 +175,9 @@ __global__ void ratio_kernel(int ncol, int use_ratio, const double* __restrict__
 }
 
 // ---- gene-major weight lists ---------------------------------------------------------------
-__global__ void w_count_kernel(int64_t n_entry, const int32_t* __restrict__ set_genes,
+__global__ void w_count_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ set_genes,
                                uint32_t* __restrict__ cnt) {
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_entry;
+    for (int64_t e = e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < e_end;
          e += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&cnt[set_genes[e]], 1u);
 }
@@ -212,15 +212,17 @@ __global__ void w_meta_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, co
     }
 }
 
-__global__ void w_fill_kernel(int64_t n_entry, int n_s0, int n_sc, const int32_t* __restrict__ set_genes,
+// entries [e_begin, e_end) of the set-major list; the stored set id is relative to col0
+__global__ void w_fill_kernel(int64_t e_begin, int64_t e_end, int n_s0, int n_sc, int col0,
+                              const int32_t* __restrict__ set_genes,
                               const float* __restrict__ set_val, const uint32_t* __restrict__ w_ptr,
                               uint32_t* __restrict__ cursor, uint16_t* __restrict__ w_col,
                               float* __restrict__ w_val) {
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_entry;
+    for (int64_t e = e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < e_end;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int g = set_genes[e];
         const uint32_t pos = w_ptr[g] + atomicAdd(&cursor[g], 1u);
-        w_col[pos] = (uint16_t)(e < n_s0 ? 0 : 1 + (e - n_s0) / n_sc);
+        w_col[pos] = (uint16_t)((e < n_s0 ? 0 : 1 + (e - n_s0) / n_sc) - col0);
         w_val[pos] = set_val[e];
     }
 }
@@ -397,6 +399,32 @@ static int upload_sets(scdrs_ctx* c, const int32_t* trait_genes, const int32_t* 
     return 0;
 }
 
+// Compact gene-major lists of the sets [col0, col1): for gene g the ids (relative to col0) and .gs
+// weights of the sets that contain it -> c->w_ptr (offsets), c->w_col, c->w_val; c->w_cursor holds the
+// per-gene counts afterwards.
+int build_gene_lists(scdrs_ctx* c, int col0, int col1) {
+    const int n_s = c->n_s, n_sc = c->n_sc, n_gene = c->n_gene;
+    const int64_t e_begin = col0 == 0 ? 0 : (int64_t)n_s + (int64_t)(col0 - 1) * n_sc;
+    const int64_t e_end = col1 == 0 ? 0 : (int64_t)n_s + (int64_t)(col1 - 1) * n_sc;
+    const int64_t n_entry = e_end - e_begin;
+    SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
+    const int nb = (int)((n_entry + 255) / 256 < 1184 ? (n_entry + 255) / 256 : 1184);
+    if (n_entry > 0) {
+        w_count_kernel<<<nb, 256, 0, c->stream>>>(e_begin, e_end, c->set_genes.as<int32_t>(), c->w_cursor.as<uint32_t>());
+        SCDRS_LAUNCH_CHECK(c);
+    }
+    SCDRS_TRY(exclusive_scan_u32(c, c->w_cursor.as<uint32_t>(), c->w_ptr.as<uint32_t>(), n_gene + 1));
+    if (n_entry > 0) {
+        SCDRS_TRY(c->stage.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+        SCDRS_CUDA(cudaMemsetAsync(c->stage.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
+        w_fill_kernel<<<nb, 256, 0, c->stream>>>(e_begin, e_end, n_s, n_sc > 0 ? n_sc : 1, col0, c->set_genes.as<int32_t>(),
+                                                 c->set_w.as<float>(), c->w_ptr.as<uint32_t>(), c->stage.as<uint32_t>(),
+                                                 c->w_col.as<uint16_t>(), c->w_val.as<float>());
+        SCDRS_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
 static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explicit_w, bool binary,
                    double gw_absmax) {
     const int ncol = c->ncol, n_s = c->n_s, n_sc = c->n_sc, n_gene = c->n_gene;
@@ -443,24 +471,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                                                             c->ratio_a.as<double>());
     SCDRS_LAUNCH_CHECK(c);
 
-    // compact gene-major lists: for gene g the ids (and .gs weights) of the sets that contain it
-    SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
-    const int nb = (int)((n_entry + 255) / 256 < 1184 ? (n_entry + 255) / 256 : 1184);
-    w_count_kernel<<<nb, 256, 0, c->stream>>>(n_entry, c->set_genes.as<int32_t>(),
-                                              c->w_cursor.as<uint32_t>());
-    SCDRS_LAUNCH_CHECK(c);
-    SCDRS_TRY(exclusive_scan_u32(c, c->w_cursor.as<uint32_t>(), c->w_ptr.as<uint32_t>(), n_gene + 1));
-    w_padded_len_kernel<<<(n_gene + 256) / 256, 256, 0, c->stream>>>(n_gene, c->w_cursor.as<uint32_t>(),
-                                                                     c->p_ptr.as<uint32_t>());
-    SCDRS_LAUNCH_CHECK(c);
-    SCDRS_CUDA(cudaMemsetAsync(c->w_cursor.p, 0, (size_t)(n_gene + 1) * sizeof(uint32_t), c->stream));
-    w_fill_kernel<<<nb, 256, 0, c->stream>>>(n_entry, n_s, n_sc > 0 ? n_sc : 1, c->set_genes.as<int32_t>(),
-                                             c->set_w.as<float>(), c->w_ptr.as<uint32_t>(),
-                                             c->w_cursor.as<uint32_t>(), c->w_col.as<uint16_t>(),
-                                             c->w_val.as<float>());
-    SCDRS_LAUNCH_CHECK(c);
-
-    // fixed-point scatter when it applies (spmm_score_fx.cu), else fp64 accumulators
+    // which scatter: fixed point when it applies (spmm_score_fx.cu), else fp64 accumulators
     bool use_fx = fx_applicable(c, ncol, explicit_w);
     if (use_fx) {
         SCDRS_TRY(fx_value_stats(c, weight_opt));
@@ -468,10 +479,14 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
                  gw_absmax < 1e30;
     }
     SCDRS_CHECK(use_fx || c->spmm_mode != 2,
-                "fixed-point scatter requested but not applicable (needs 1 + n_ctrl <= %d, a trait prepared by "
-                "scdrs_trait_raw and max|x*base| <= 128 mean|x*base|)", kFxMaxCol);
-    if (use_fx) return fx_layout(c, binary, binary ? 1.0 : gw_absmax);
+                "fixed-point scatter requested but not applicable (needs a trait prepared by scdrs_trait_raw, "
+                "1 + n_ctrl <= %d and max|x*base| <= 128 mean|x*base|)", kFxMaxCol * kFxMaxTiles);
+    if (use_fx) return fx_prepare(c, binary, binary ? 1.0 : gw_absmax);
 
+    SCDRS_TRY(build_gene_lists(c, 0, ncol));
+    w_padded_len_kernel<<<(n_gene + 256) / 256, 256, 0, c->stream>>>(n_gene, c->w_cursor.as<uint32_t>(),
+                                                                     c->p_ptr.as<uint32_t>());
+    SCDRS_LAUNCH_CHECK(c);
     // padded size: every non-empty gene rounds up to a multiple of 64 slots
     const int64_t n_slot_max = n_entry + 63 * (int64_t)(n_gene < n_entry ? n_gene : n_entry) + 64;
     SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
@@ -480,6 +495,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     w_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->w_ptr.as<uint32_t>(), c->p_ptr.as<uint32_t>(), c->gbase.as<double>(),
                                                                c->p_meta.as<GeneInfo>());
     SCDRS_LAUNCH_CHECK(c);
+    const int nb = (int)((n_slot_max + 255) / 256 < 1184 ? (n_slot_max + 255) / 256 : 1184);
     w_pad_init_kernel<<<nb, 256, 0, c->stream>>>(n_slot_max, c->p_col.as<uint16_t>(),
                                                  binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);

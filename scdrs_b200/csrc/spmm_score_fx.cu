@@ -20,7 +20,9 @@
 //     to one word come from the same lane in program order (no warp barriers).  ceil(n / 32) rounds
 //     per gene suffice in practice: 2 rounds = 4 wavefronts per stored entry instead of ~14.
 //
-// Used when 1 + n_ctrl <= 1024 and max|x * base| <= 128 * mean|x * base|; otherwise the fp64 kernel runs.
+// Score matrices wider than 1024 columns are produced in column tiles of 1024 sets (own lists, own pass
+// over X; the first tile fixes the row reference).  Used when max|x * base| <= 128 * mean|x * base|;
+// otherwise, and for explicit-weight calls, the fp64 kernel runs.
 #include <math.h>
 
 #include "common.cuh"
@@ -90,7 +92,7 @@ __global__ void fx_vstat_final_kernel(int nb, double* __restrict__ part) {
 
 bool fx_applicable(scdrs_ctx* c, int ncol, bool explicit_w) {
     // n_gene bounds the stored entries of a row, which keeps the 32-bit column totals exact (see the kernel)
-    return c->spmm_mode != 1 && !explicit_w && ncol <= kFxMaxCol && c->nnz > 0 && c->n_gene < (1 << 18);
+    return c->spmm_mode != 1 && !explicit_w && ncol <= kFxMaxCol * kFxMaxTiles && c->nnz > 0 && c->n_gene < (1 << 18);
 }
 
 // max and mean of |x * base_g| over the stored entries; c->gbase must hold the base weights of
@@ -311,11 +313,11 @@ __global__ void fx_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, c
 // (an estimate of its mean raw score) without a pass over the per-column constants.
 // out[0] = mean colscale, out[1] = mean covm, out[2 + kk] = mean covM[kk, :].  One block, fixed order.
 __global__ void __launch_bounds__(256)
-fx_scalars_kernel(int ncol, int k, const double* __restrict__ colscale, const double* __restrict__ covm,
+fx_scalars_kernel(int ncol, int cov_stride, int k, const double* __restrict__ colscale, const double* __restrict__ covm,
                   const double* __restrict__ covM, double* __restrict__ out) {
     __shared__ double sh[256];
     for (int q = 0; q < 2 + k; ++q) {
-        const double* src = q == 0 ? colscale : (q == 1 ? covm : covM + (size_t)(q - 2) * ncol);
+        const double* src = q == 0 ? colscale : (q == 1 ? covm : covM + (size_t)(q - 2) * cov_stride);
         double part = 0.0;
         if (q != 1 || k > 0)
             for (int j = threadIdx.x; j < ncol; j += 256) part += src[j];
@@ -330,13 +332,13 @@ fx_scalars_kernel(int ncol, int k, const double* __restrict__ colscale, const do
     }
 }
 
-// Called by build_w after the compact gene-major lists (w_ptr, w_col, w_val) exist.
-int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax) {
-    const int n_gene = c->n_gene;
-    const int64_t n_entry = (int64_t)c->n_s + (int64_t)c->n_ctrl * c->n_sc;
-    // worst case: every round of a gene holds one entry
-    const int64_t n_slot_max = 32 * n_entry + 64 * (int64_t)n_gene + 128;
-    SCDRS_CHECK(n_slot_max < ((int64_t)1 << 30), "gene-set lists too large for the fixed-point layout");
+// Scale and tiling of the fixed-point scatter for the trait whose per-set constants build_w has just
+// computed.  A score matrix wider than kFxMaxCol columns is produced in column tiles (sets [1024 T,
+// 1024 (T + 1))), each with its own gene-major lists and its own pass over X; with one tile the lists
+// are built here, otherwise per tile right before its pass (fx_spmm).
+static int fx_build_tile(scdrs_ctx* c, int tile);
+
+int fx_prepare(scdrs_ctx* c, bool binary, double gw_absmax) {
     SCDRS_CHECK(c->fx_vmax > 0.0 && gw_absmax > 0.0 && isfinite(c->fx_vmax) && isfinite(gw_absmax),
                 "fixed-point scatter needs finite non-zero values");
     int shift = ilogb(ldexp(1.0, kFxItemBits) / (c->fx_vmax * gw_absmax));
@@ -344,7 +346,30 @@ int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax) {
     if (shift < -200) shift = -200;
     c->fx_shift = shift;
     c->fx_gwmax = (float)gw_absmax * 1.000001f;
-    SCDRS_TRY(c->w_code.reserve((size_t)n_entry * sizeof(uint16_t)));
+    c->fx_n_tile = (c->ncol + kFxMaxCol - 1) / kFxMaxCol;
+    c->w_binary = binary;
+    c->w_fx = true;
+    c->fx_tile0_built = false;
+    if (c->fx_n_tile == 1) {
+        SCDRS_TRY(fx_build_tile(c, 0));
+        c->fx_tile0_built = true;
+    }
+    return 0;
+}
+
+static int fx_build_tile(scdrs_ctx* c, int tile) {
+    const int n_gene = c->n_gene;
+    const bool binary = c->w_binary;
+    const int col0 = tile * kFxMaxCol, col1 = (col0 + kFxMaxCol < c->ncol) ? col0 + kFxMaxCol : c->ncol;
+    const int ncol_t = col1 - col0;
+    const int64_t e_begin = col0 == 0 ? 0 : (int64_t)c->n_s + (int64_t)(col0 - 1) * c->n_sc;
+    const int64_t e_end = (int64_t)c->n_s + (int64_t)(col1 - 1) * c->n_sc;
+    const int64_t n_entry = e_end - e_begin;
+    // worst case: every round of a gene holds one entry
+    const int64_t n_slot_max = 32 * n_entry + 64 * (int64_t)n_gene + 128;
+    SCDRS_CHECK(n_slot_max < ((int64_t)1 << 30), "gene-set lists too large for the fixed-point layout");
+    SCDRS_TRY(build_gene_lists(c, col0, col1));
+    SCDRS_TRY(c->w_code.reserve((size_t)(n_entry > 0 ? n_entry : 1) * sizeof(uint16_t)));
     SCDRS_TRY(c->w_rounds.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
     if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
@@ -365,13 +390,15 @@ int fx_layout(scdrs_ctx* c, bool binary, double gw_absmax) {
         c->w_code.as<uint16_t>(), c->w_val.as<float>(), c->p_col.as<uint16_t>(), binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
     fx_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(), c->w_rounds.as<uint32_t>(),
-                                                               c->gbase.as<double>(), ldexp(1.0, shift), c->p_meta.as<GeneInfo>());
+                                                               c->gbase.as<double>(), ldexp(1.0, c->fx_shift), c->p_meta.as<GeneInfo>());
     SCDRS_LAUNCH_CHECK(c);
-    SCDRS_TRY(c->fx_scal.reserve((size_t)(2 + (c->k > 0 ? c->k : 0)) * sizeof(double)));
-    fx_scalars_kernel<<<1, 256, 0, c->stream>>>(c->ncol, c->k, c->colscale.as<double>(), c->covm.as<double>(),
-                                                 c->covM.as<double>(), c->fx_scal.as<double>());
-    SCDRS_LAUNCH_CHECK(c);
-    c->w_fx = true;
+    if (tile == 0) {
+        // column means of the per-set constants over the first tile: they place the row reference
+        SCDRS_TRY(c->fx_scal.reserve((size_t)(2 + (c->k > 0 ? c->k : 0)) * sizeof(double)));
+        fx_scalars_kernel<<<1, 256, 0, c->stream>>>(ncol_t, c->ncol, c->k, c->colscale.as<double>(), c->covm.as<double>(),
+                                                     c->covM.as<double>(), c->fx_scal.as<double>());
+        SCDRS_LAUNCH_CHECK(c);
+    }
     return 0;
 }
 
@@ -434,7 +461,7 @@ __device__ __forceinline__ uint32_t fx_ldg_pinned(const uint32_t* p) {
 // registers = 20 warps per SM.
 template <bool WEIGHTED, int D>
 __global__ void __launch_bounds__(kFxWarpsPerBlock * 32, kFxBlocksPerSM)
-spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict__ indptr,
+spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, int ld, const int64_t* __restrict__ indptr,
                      const int32_t* __restrict__ indices, const float* __restrict__ data,
                      const GeneInfo* __restrict__ ginfo, const uint32_t* __restrict__ p_col32,
                      const float2* __restrict__ p_val2, const double* __restrict__ colscale,
@@ -619,11 +646,16 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
-        double ref = ((double)isum * inv_scale) * scal[0] / (double)ncol;
-        if (k > 0) {
-            double cterm = scal[1];
-            for (int kk = 0; kk < k; ++kk) cterm = fma(cov_mat[row * k + kk], scal[2 + kk], cterm);
-            ref += cterm;
+        double ref;
+        if (write_ref) {
+            ref = ((double)isum * inv_scale) * scal[0] / (double)ncol;
+            if (k > 0) {
+                double cterm = scal[1];
+                for (int kk = 0; kk < k; ++kk) cterm = fma(cov_mat[row * k + kk], scal[2 + kk], cterm);
+                ref += cterm;
+            }
+        } else {
+            ref = row_ref[row];       // later column tiles share the reference the first tile chose
         }
         float* out = dev_mat + row * (int64_t)ld;
 #pragma unroll 1
@@ -636,7 +668,7 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
                 if (k > 0) {
                     double cterm = covm[j];
                     for (int kk = 0; kk < k; ++kk)
-                        cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * ncol + j], cterm);
+                        cterm = fma(cov_mat[row * k + kk], covM[(size_t)kk * cov_stride + j], cterm);
                     v += cterm;
                 }
                 out[j] = (v == 0.0) ? __int_as_float(0x7fc00000) : (float)(v - ref);
@@ -644,15 +676,14 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int ld, const int64_t* __restrict
             accw[ia] = 0u;
             accw[ib] = 0u;
         }
-        if (lane == 0) row_ref[row] = ref;
+        if (lane == 0 && write_ref) row_ref[row] = ref;
     }
 }
 
 constexpr int kFxDepthBinary = 8, kFxDepthWeighted = 4;
 
 int fx_spmm(scdrs_ctx* c) {
-    const int ncol = c->ncol;
-    SCDRS_CHECK(c->w_fx && ncol <= kFxMaxCol, "fixed-point lists were not built");
+    SCDRS_CHECK(c->w_fx && c->ncol <= kFxMaxCol * kFxMaxTiles, "fixed-point lists were not built");
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
     const int wpb = kFxWarpsPerBlock, per_sm = kFxBlocksPerSM;
@@ -669,19 +700,27 @@ int fx_spmm(scdrs_ctx* c) {
     if (grid < 1) grid = 1;
     const double inv_scale = ldexp(1.0, -c->fx_shift);
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (c->w_binary)
-        spmm_score_fx_kernel<false, kFxDepthBinary><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-            c->n_cell, ncol, c->ld, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
-            c->p_col.as<uint32_t>(), nullptr, c->colscale.as<double>(), inv_scale, c->fx_gwmax, c->k,
-            c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->fx_scal.as<double>(),
-            c->dev_mat.as<float>(), c->row_ref.as<double>());
-    else
-        spmm_score_fx_kernel<true, kFxDepthWeighted><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-            c->n_cell, ncol, c->ld, c->indptr, c->indices, c->data, c->p_meta.as<GeneInfo>(),
-            c->p_col.as<uint32_t>(), c->p_val.as<float2>(), c->colscale.as<double>(), inv_scale, c->fx_gwmax,
-            c->k, c->cov_mat.as<double>(), c->covM.as<double>(), c->covm.as<double>(), c->fx_scal.as<double>(),
-            c->dev_mat.as<float>(), c->row_ref.as<double>());
-    SCDRS_LAUNCH_CHECK(c);
+    for (int tile = 0; tile < c->fx_n_tile; ++tile) {
+        // with several column tiles the gene-major lists of a tile are built right before its pass over X
+        if (!(tile == 0 && c->fx_tile0_built)) SCDRS_TRY(fx_build_tile(c, tile));
+        const int col0 = tile * kFxMaxCol;
+        const int ncol_t = (col0 + kFxMaxCol < c->ncol ? col0 + kFxMaxCol : c->ncol) - col0;
+        if (c->w_binary)
+            spmm_score_fx_kernel<false, kFxDepthBinary><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+                c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
+                c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), nullptr, c->colscale.as<double>() + col0, inv_scale,
+                c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0, c->covm.as<double>() + col0,
+                c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0, c->row_ref.as<double>());
+        else
+            spmm_score_fx_kernel<true, kFxDepthWeighted><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+                c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
+                c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), c->p_val.as<float2>(), c->colscale.as<double>() + col0,
+                inv_scale, c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0,
+                c->covm.as<double>() + col0, c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0,
+                c->row_ref.as<double>());
+        SCDRS_LAUNCH_CHECK(c);
+    }
+    if (c->fx_n_tile > 1) c->fx_tile0_built = false;     // the lists now belong to the last tile
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->trait_ready = true;
     return 0;

@@ -549,19 +549,26 @@ def test_fixed_point_scatter_against_fp64_and_oracle(native_lib, n_gene, n_trait
     _compare_with_reference(fx, ref, n_ctrl, n_cell)
 
 
-def test_fixed_point_scatter_falls_back_on_outliers_and_wide_matrices(native_lib):
-    """One stored value 1e5 times the others would cost the fixed-point scale 17 bits: auto mode runs
-    the fp64 kernel (and "fixed" refuses); so does 1 + n_ctrl > 1024."""
+def test_fixed_point_scatter_column_tiles_and_outlier_fallback(native_lib):
+    """1 + n_ctrl > 1024 is scattered in column tiles of 1024 sets (here two) and must agree with the
+    fp64 kernel and the oracle.  One stored value 1e5 times the others would cost the fixed-point scale
+    17 bits: auto mode then runs the fp64 kernel (and "fixed" refuses)."""
     from scdrs_b200 import _device, synth
     from scdrs_b200.loess1d import loess
 
     adata, cov = synth.make_adata(300, 1500, density=0.1, seed=6)
     orc.preprocess(adata, cov=cov, loess_impl=loess)
     genes, w = synth.make_traits(adata.var_names, 1, 100, weighted=False, seed=10)["trait_00"]
-    df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=1100)
+    kw = dict(n_ctrl=1100, return_ctrl_raw_score=True, return_ctrl_norm_score=True)
+    fx, kind = _score_in_mode("auto", adata, genes, w, **kw)
+    assert kind[0] == "fixed"
+    f64, kind = _score_in_mode("f64", adata, genes, w, **kw)
     assert kind[0] == "f64"
-    with pytest.raises(RuntimeError, match="fixed-point scatter requested"):
-        _score_in_mode("fixed", adata, genes, w, n_ctrl=1100)
+    cr = ["ctrl_raw_score_%d" % i for i in range(1100)]
+    top = float(np.abs(f64[cr].values).max())
+    assert np.allclose(fx[cr].values, f64[cr].values, rtol=1e-6, atol=2e-7 * top)
+    _check_counts_self_consistent(fx, 1100)
+    _compare_with_reference(fx, orc.score_cell(adata, genes, gene_weight=w, **kw), 1100, 300)
     df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=50)
     assert kind[0] == "fixed"
     X = adata.X.copy()
@@ -572,6 +579,8 @@ def test_fixed_point_scatter_falls_back_on_outliers_and_wide_matrices(native_lib
     df, kind = _score_in_mode("auto", adata, genes, w, n_ctrl=50)
     assert kind[0] == "f64"
     _compare_with_reference(df, ref, 50, 300)
+    with pytest.raises(RuntimeError, match="fixed-point scatter requested"):
+        _score_in_mode("fixed", adata, genes, w, n_ctrl=50)
 
 
 def test_score_traits_equal_score_cell(native_lib):
