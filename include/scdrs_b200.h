@@ -45,8 +45,8 @@ int64_t scdrs_ctx_launch_count(scdrs_ctx* ctx);
 int scdrs_ctx_last_timing(scdrs_ctx* ctx, float* spmm_ms, float* trait_ms);
 
 /* Arithmetic of the raw-score scatter (phase 1).  mode 0 (default): exact fixed-point integer sums
- * when 1 + n_ctrl <= 1024 and the stored values have no extreme outliers, fp64 accumulators
- * otherwise; mode 1: always fp64; mode 2: fixed point or fail.  Both reproduce the reference's
+ * when the stored values have no extreme outliers (in column tiles of 1024 sets when
+ * 1 + n_ctrl > 1024), fp64 accumulators otherwise; mode 1: always fp64; mode 2: fixed point or fail.  Both reproduce the reference's
  * float64 _compute_raw_score (scdrs/method.py:377-400) far inside the 1e-5 tolerance. */
 int scdrs_ctx_set_spmm_mode(scdrs_ctx* ctx, int32_t mode);
 /* which arithmetic the last prepared trait uses, and log2 of the fixed-point scale */
