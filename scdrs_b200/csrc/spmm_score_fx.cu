@@ -120,17 +120,19 @@ int fx_value_stats(scdrs_ctx* c, int weight_opt) {
 // when both are full, along a shortest augmenting path (breadth-first over banks, moving resident
 // entries to their other bank); R starts at ceil(n / 32) and grows only when no path exists.  Longer
 // lists (and R > 8) use plain two-choice greedy.  code[t] = (round << 1) | array of entry t.
-constexpr int kAsgThreads = 64;
+constexpr int kAsgThreads = 8;      // genes per block: ONE gene per warp (lane 0 works), so divergent genes do not serialise each other
+constexpr int kAsgBlock = kAsgThreads * 32;
 constexpr int kAsgMaxLen = 128;
 constexpr int kAsgMaxR = 8;
 constexpr int kAsgBytesPerThread = 2 * 32 * kAsgMaxR + 32 + 32 + 32 + 64;
 
-__global__ void __launch_bounds__(kAsgThreads)
+__global__ void __launch_bounds__(kAsgBlock)
 fx_assign_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint16_t* __restrict__ w_col,
                  uint16_t* __restrict__ code, uint32_t* __restrict__ rounds) {
     extern __shared__ unsigned char asg_sm[];
     constexpr int T = kAsgThreads;
-    const int tid = threadIdx.x;
+    if ((threadIdx.x & 31) != 0) return;
+    const int tid = threadIdx.x >> 5;
     unsigned char* sm_slot = asg_sm;                              // [32 * kAsgMaxR][T] entry in the slot
     unsigned char* sm_alt = sm_slot + 32 * kAsgMaxR * T;          // [32 * kAsgMaxR][T] its other bank
     unsigned char* sm_par = sm_alt + 32 * kAsgMaxR * T;           // [32][T]
@@ -379,7 +381,7 @@ static int fx_build_tile(scdrs_ctx* c, int tile) {
         SCDRS_CUDA(cudaFuncSetAttribute(fx_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asg_smem));
         attr = true;
     }
-    fx_assign_kernel<<<(n_gene + kAsgThreads - 1) / kAsgThreads, kAsgThreads, asg_smem, c->stream>>>(
+    fx_assign_kernel<<<(n_gene + kAsgThreads - 1) / kAsgThreads, kAsgBlock, asg_smem, c->stream>>>(
         n_gene, c->w_ptr.as<uint32_t>(), c->w_col.as<uint16_t>(), c->w_code.as<uint16_t>(), c->w_rounds.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     fx_plen_kernel<<<(n_gene + 256) / 256, 256, 0, c->stream>>>(n_gene, c->w_rounds.as<uint32_t>(), c->p_ptr.as<uint32_t>());
