@@ -132,7 +132,7 @@ static void release_all(scdrs_ctx* c) {
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
-                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal};
+                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr};
     for (DevBuf* b : bufs) b->release();
 }
 

@@ -91,7 +91,7 @@ struct scdrs_ctx {
     int fx_stat_key = -1;     // weight_opt the value statistics below were computed for (-1: none)
     double fx_vmax = 0.0, fx_vmean = 0.0;   // max and mean of |x * base_g| over the stored entries
     float fx_gwmax = 1.f;
-    scdrs::DevBuf w_code, w_rounds, fx_part;
+    scdrs::DevBuf w_code, w_rounds, fx_part, fx_rowctr;
     scdrs::DevBuf dev_mat;   // float [n_cell x ld]: raw score minus the row reference; NaN = exact 0
     scdrs::DevBuf row_ref;   // double [n_cell]
     scdrs::DevBuf partial;   // double scratch for per-CTA column partials

@@ -469,7 +469,8 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, in
                      const float2* __restrict__ p_val2, const double* __restrict__ colscale,
                      double inv_scale, float gwmax, int k, const double* __restrict__ cov_mat,
                      const double* __restrict__ covM, const double* __restrict__ covm,
-                     const double* __restrict__ scal, float* __restrict__ dev_mat, double* __restrict__ row_ref) {
+                     const double* __restrict__ scal, float* __restrict__ dev_mat, double* __restrict__ row_ref,
+                     unsigned long long* __restrict__ next_row) {
     static_assert(D <= kFxMaxDepth && (kFxItemCap % D) == 0, "pipeline depth");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -482,7 +483,14 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, in
     for (int i = lane; i < 2 * kFxNB / 4; i += 32) reinterpret_cast<uint4*>(accw)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
 
-    for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_cell; row += (int64_t)gridDim.x * wpb) {
+    // rows are handed out dynamically (one atomic per cell): cells differ in stored entries and every
+    // warp should finish at the same time; the result of a cell does not depend on who computes it
+    (void)wpb;
+    for (;;) {
+        long long row_l = 0;
+        if (lane == 0) row_l = (long long)atomicAdd(next_row, 1ull);
+        const int64_t row = __shfl_sync(0xffffffffu, row_l, 0);
+        if (row >= n_cell) break;
         int hi[kFxNB / 32];
 #pragma unroll
         for (int t = 0; t < kFxNB / 32; ++t) hi[t] = 0;
@@ -701,6 +709,8 @@ int fx_spmm(scdrs_ctx* c) {
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     const double inv_scale = ldexp(1.0, -c->fx_shift);
+    SCDRS_TRY(c->fx_rowctr.reserve((size_t)kFxMaxTiles * sizeof(unsigned long long)));
+    SCDRS_CUDA(cudaMemsetAsync(c->fx_rowctr.p, 0, (size_t)kFxMaxTiles * sizeof(unsigned long long), c->stream));
     if (c->timed_spmm) SCDRS_CUDA(cudaEventRecord(c->ev[0], c->stream));
     for (int tile = 0; tile < c->fx_n_tile; ++tile) {
         // with several column tiles the gene-major lists of a tile are built right before its pass over X
@@ -712,14 +722,15 @@ int fx_spmm(scdrs_ctx* c) {
                 c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
                 c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), nullptr, c->colscale.as<double>() + col0, inv_scale,
                 c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0, c->covm.as<double>() + col0,
-                c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0, c->row_ref.as<double>());
+                c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0, c->row_ref.as<double>(),
+                c->fx_rowctr.as<unsigned long long>() + tile);
         else
             spmm_score_fx_kernel<true, kFxDepthWeighted><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
                 c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
                 c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), c->p_val.as<float2>(), c->colscale.as<double>() + col0,
                 inv_scale, c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0,
                 c->covm.as<double>() + col0, c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0,
-                c->row_ref.as<double>());
+                c->row_ref.as<double>(), c->fx_rowctr.as<unsigned long long>() + tile);
         SCDRS_LAUNCH_CHECK(c);
     }
     if (c->fx_n_tile > 1) c->fx_tile0_built = false;     // the lists now belong to the last tile
