@@ -1,4 +1,4 @@
-"""Does a small kernel on another stream run while the scatter kernel is resident? (scratch diagnostics)"""
+"""Probe (historical): needed the twin-context experiment, which was measured and reverted; kept for the record."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

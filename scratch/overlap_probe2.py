@@ -1,4 +1,4 @@
-"""Do the twin context's post-processing kernels run while the main context's scatter kernel is resident?"""
+"""Probe (historical): needed the twin-context experiment, which was measured and reverted; kept for the record."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
