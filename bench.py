@@ -419,7 +419,7 @@ def main():
         if "lsu_data_pipe_pct_of_peak" in prof:
             # the resource that actually binds the scatter: the SM's LSU data pipe takes one wavefront per
             # clock; floor = wavefronts of the ncu capture / (SMs x clock), against the live launch time
-            wf = float(prof["lsu_data_pipe_pct_of_peak"]) / 100.0 * 9.227e-3 * 1.965e9 * 148
+            wf = float(prof["lsu_data_pipe_pct_of_peak"]) / 100.0 * float(prof.get("capture_ms", 9.227)) * 1e-3 * 1.965e9 * 148
             floor_ms = wf / (148 * 1.965e9) * 1e3
             binding = {"resource": "LSU data pipe (shared-memory + L1 wavefronts, one per SM per clock)",
                        "wavefronts_per_launch": wf, "floor_ms": floor_ms,
