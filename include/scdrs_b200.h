@@ -59,6 +59,22 @@ int scdrs_set_csr_host(scdrs_ctx* ctx, int64_t n_cell, int32_t n_gene, const int
                        const int32_t* indices, const float* data);
 int scdrs_set_csr_dev(scdrs_ctx* ctx, int64_t n_cell, int32_t n_gene, const int64_t* dev_indptr,
                       const int32_t* dev_indices, const float* dev_data);
+/* ---- the step before the path: load_h5ad's checks, filters and normalisation -----------------
+ * scdrs/util.py:72-91 (NaN / negative checks; scanpy filter_cells(min_genes), filter_genes(min_cells),
+ * normalize_per_cell(counts_per_cell_after = target_sum, cells with a total < 1 dropped), log1p) on the
+ * resident CSR matrix, which is replaced by the processed one and stays resident.  has_nan / has_negative:
+ * the reference raises ValueError for either; nothing is modified then.  With both flags 0 only the checks
+ * run.  Host outputs, indexed by ORIGINAL cell / gene: keep_cell[n_cell], keep_gene[n_gene] (final
+ * survivors), n_genes_per_cell[n_cell] (stored entries), n_cells_per_gene[n_gene] (over the cells that
+ * passed min_genes), n_counts[n_cell] (total over the surviving genes; valid for cells that passed
+ * min_genes).  n_cell_out / n_gene_out / nnz_out: shape of the matrix now resident. */
+int scdrs_preprocess_counts(scdrs_ctx* ctx, int32_t flag_filter_data, int32_t min_genes, int32_t min_cells,
+                            int32_t flag_raw_count, double target_sum, int32_t* has_nan, int32_t* has_negative,
+                            int64_t* n_cell_out, int32_t* n_gene_out, int64_t* nnz_out, uint8_t* keep_cell,
+                            uint8_t* keep_gene, int32_t* n_genes_per_cell, int32_t* n_cells_per_gene, float* n_counts);
+/* download the resident CSR matrix (host arrays sized from the shape the context reports) */
+int scdrs_get_csr(scdrs_ctx* ctx, int64_t* indptr, int32_t* indices, float* data);
+
 /* GENE_STATS["var"], GENE_STATS["var_tech"] (scdrs/method.py:369-371, 192-195); host, n_gene each */
 int scdrs_set_gene_stats(scdrs_ctx* ctx, const double* var, const double* var_tech);
 /* implicit covariate correction terms COV_MAT (n_cell x k), COV_BETA (n_gene x k, = -beta) and

@@ -104,6 +104,26 @@ class DeviceState:
         self.cov_fp = fp
 
 
+def adopt_context(adata, ctx):
+    """Bind a context that already holds ``adata.X`` on the device (``util.load_h5ad``) to ``adata``."""
+    st = DeviceState.__new__(DeviceState)
+    st.ctx = ctx
+    ctx.set_spmm_mode(_SPMM_MODE[0])
+    st.x_fp = _x_fingerprint(adata.X)
+    st.cov_fp = None
+    st.h2d_bytes = 0
+    st.bins_cache = {}
+    old = _STATES.pop(id(adata), None)
+    if old is not None:
+        old.close()
+    _STATES[id(adata)] = st
+    try:
+        weakref.finalize(adata, _drop, id(adata))
+    except TypeError:
+        pass
+    return st
+
+
 def get_state(adata, device=None):
     key = id(adata)
     st = _STATES.get(key)

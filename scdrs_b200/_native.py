@@ -33,6 +33,11 @@ SIGNATURES = {
     "scdrs_ctx_last_spmm_kind": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scdrs_set_csr_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_set_csr_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_preprocess_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_get_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_set_gene_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_set_cov": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_trait_raw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -135,6 +140,31 @@ class Context:
         check(self._L.scdrs_set_csr_dev(self._h, int(n_cell), int(n_gene), int(d_indptr), int(d_indices), int(d_data)))
         self.n_cell, self.n_gene = int(n_cell), int(n_gene)
         self._keep = list(keep)
+
+    def preprocess_counts(self, flag_filter_data, min_genes, min_cells, flag_raw_count, target_sum=1e4):
+        """load_h5ad's checks / filters / normalisation on the resident matrix (scdrs_preprocess_counts).
+        Returns a dict; the processed matrix stays resident (``get_csr`` downloads it)."""
+        n_cell, n_gene = self.n_cell, self.n_gene
+        out = dict(keep_cell=np.zeros(n_cell, np.uint8), keep_gene=np.zeros(n_gene, np.uint8),
+                   n_genes=np.zeros(n_cell, np.int32), n_cells=np.zeros(n_gene, np.int32),
+                   n_counts=np.zeros(n_cell, np.float32))
+        has_nan, has_neg = C.c_int32(), C.c_int32()
+        nc, ng, nz = C.c_int64(), C.c_int32(), C.c_int64()
+        check(self._L.scdrs_preprocess_counts(
+            self._h, int(bool(flag_filter_data)), int(min_genes), int(min_cells), int(bool(flag_raw_count)),
+            float(target_sum), C.byref(has_nan), C.byref(has_neg), C.byref(nc), C.byref(ng), C.byref(nz),
+            ptr(out["keep_cell"]), ptr(out["keep_gene"]), ptr(out["n_genes"]), ptr(out["n_cells"]), ptr(out["n_counts"])))
+        out.update(has_nan=bool(has_nan.value), has_negative=bool(has_neg.value), n_cell=int(nc.value),
+                   n_gene=int(ng.value), nnz=int(nz.value))
+        if not (out["has_nan"] or out["has_negative"]):
+            self.n_cell, self.n_gene = out["n_cell"], out["n_gene"]
+        return out
+
+    def get_csr(self, nnz):
+        indptr = np.empty(self.n_cell + 1, np.int64)
+        indices, data = np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+        check(self._L.scdrs_get_csr(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        return indptr, indices, data
 
     def set_gene_stats(self, var, var_tech):
         var, var_tech = as_c(var, np.float64), as_c(var_tech, np.float64)

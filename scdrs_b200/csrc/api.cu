@@ -325,6 +325,36 @@ int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_
     return 0;
 }
 
+int scdrs_preprocess_counts(scdrs_ctx* c, int32_t flag_filter_data, int32_t min_genes, int32_t min_cells,
+                            int32_t flag_raw_count, double target_sum, int32_t* has_nan, int32_t* has_negative,
+                            int64_t* n_cell_out, int32_t* n_gene_out, int64_t* nnz_out, uint8_t* keep_cell,
+                            uint8_t* keep_gene, int32_t* n_genes_per_cell, int32_t* n_cells_per_gene, float* n_counts) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(has_nan && has_negative && n_cell_out && n_gene_out && nnz_out, "null output pointer");
+    SCDRS_CHECK((!flag_filter_data && !flag_raw_count) ||
+                    (keep_cell && keep_gene && n_genes_per_cell && n_cells_per_gene && n_counts),
+                "null output arrays");
+    SCDRS_CHECK(!flag_raw_count || target_sum > 0, "target_sum must be positive");
+    int hn = 0, hneg = 0;
+    const int rc = counts_preprocess(c, flag_filter_data ? 1 : 0, min_genes, min_cells, flag_raw_count ? 1 : 0,
+                                     target_sum, &hn, &hneg, n_cell_out, n_gene_out, nnz_out, keep_cell, keep_gene,
+                                     n_genes_per_cell, n_cells_per_gene, n_counts);
+    *has_nan = hn;
+    *has_negative = hneg;
+    return rc;
+}
+
+int scdrs_get_csr(scdrs_ctx* c, int64_t* indptr, int32_t* indices, float* data) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    SCDRS_CHECK(indptr && (c->nnz == 0 || (indices && data)), "null output pointer");
+    SCDRS_TRY(d2h(c, indptr, c->indptr, (size_t)(c->n_cell + 1) * sizeof(int64_t)));
+    SCDRS_TRY(d2h(c, indices, c->indices, (size_t)c->nnz * sizeof(int32_t)));
+    SCDRS_TRY(d2h(c, data, c->data, (size_t)c->nnz * sizeof(float)));
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int scdrs_set_gene_stats(scdrs_ctx* c, const double* var, const double* var_tech) {
     CTX_GUARD(c);
     SCDRS_CHECK(c->indptr != nullptr, "set the expression matrix first");

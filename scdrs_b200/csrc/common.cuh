@@ -162,6 +162,12 @@ int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, int c
 
 int gene_mean_xtc(scdrs_ctx* c, int k, const double* dev_cov, float* dev_gmean32, double* dev_xtc);
 
+// ---- counts_pp.cu ---------------------------------------------------------------------------
+int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells, int do_norm, double target_sum,
+                      int* has_nan, int* has_negative, int64_t* n_cell_out, int32_t* n_gene_out, int64_t* nnz_out,
+                      uint8_t* h_keep_cell, uint8_t* h_keep_gene, int32_t* h_n_genes, int32_t* h_n_cells,
+                      float* h_n_counts);
+
 // ---- scan (empi_null.cu) --------------------------------------------------------------------
 int exclusive_scan_u32(scdrs_ctx* c, const uint32_t* in, uint32_t* out, int64_t n);
 int exclusive_scan_u64(scdrs_ctx* c, const unsigned long long* in, unsigned long long* out,

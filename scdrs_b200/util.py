@@ -29,10 +29,6 @@ def str_or_list_like(x):
     return "others"
 
 
-def _nnz_per_row(X):
-    return np.diff(X.indptr) if sparse.issparse(X) else (X != 0).sum(axis=1)
-
-
 def load_h5ad(h5ad_file, flag_filter_data=False, flag_raw_count=True, min_genes=250, min_cells=50):
     """Load an h5ad file, check it, optionally filter and normalise it (scdrs/util.py:46-92).
 
@@ -41,46 +37,85 @@ def load_h5ad(h5ad_file, flag_filter_data=False, flag_raw_count=True, min_genes=
     keeps genes expressed in at least ``min_cells`` cells (adds ``var["n_cells"]``);
     ``normalize_per_cell(counts_per_cell_after=1e4)`` drops cells with fewer than 1 count, stores
     ``obs["n_counts"]`` and scales each cell to 1e4 counts; ``log1p`` is the natural log.
+
+    Sparse matrices take the device path (``scdrs_preprocess_counts``): the raw matrix is uploaded
+    once, checked, filtered and normalised on the GPU, and stays resident for ``preprocess`` and
+    ``score_cell`` (no second upload); the processed matrix is also downloaded into ``adata.X``.  The
+    host restatement of the same steps lives in ``oracle/h5ad_oracle.py`` and is what the tests
+    compare with.  Dense matrices (not a scDRS use case at scale) are handled with numpy.
     """
     adata = read_h5ad(h5ad_file)
-    if np.isnan(adata.X.sum()):
-        raise ValueError(
-            "h5ad expression matrix should not contain NaN. Please impute them beforehand."
-        )
-    if (adata.X < 0).sum() > 0:
-        raise ValueError(
-            "h5ad expression matrix should not contain negative values. "
-            "This is because in the preprocessing step, "
-            "scDRS models the gene-level log mean-variance relationship. "
-            "See scdrs.pp.compute_stats for details."
-        )
+    return preprocess_counts(adata, flag_filter_data, flag_raw_count, min_genes, min_cells)
+
+
+_ERR_NAN = "h5ad expression matrix should not contain NaN. Please impute them beforehand."
+_ERR_NEG = (
+    "h5ad expression matrix should not contain negative values. "
+    "This is because in the preprocessing step, "
+    "scDRS models the gene-level log mean-variance relationship. "
+    "See scdrs.pp.compute_stats for details."
+)
+
+
+def preprocess_counts(adata, flag_filter_data=False, flag_raw_count=True, min_genes=250, min_cells=50):
+    """The checks / filters / normalisation of ``load_h5ad`` on an AnnData already in memory."""
+    if not sparse.issparse(adata.X):
+        return _preprocess_counts_dense(adata, flag_filter_data, flag_raw_count, min_genes, min_cells)
+    from . import _device, _native
+
+    indptr, indices, data = _device.to_csr_parts(adata.X)
+    ctx = _native.Context(_device._DEFAULT_DEVICE[0])
+    try:
+        ctx.set_csr_host(indptr, indices, data, adata.shape[1])
+        out = ctx.preprocess_counts(flag_filter_data, min_genes, min_cells, flag_raw_count)
+        if out["has_nan"]:
+            raise ValueError(_ERR_NAN)
+        if out["has_negative"]:
+            raise ValueError(_ERR_NEG)
+        if flag_filter_data or flag_raw_count:
+            keep_c, keep_g = out["keep_cell"].astype(bool), out["keep_gene"].astype(bool)
+            ip, ix, da = ctx.get_csr(out["nnz"])
+            X = sparse.csr_matrix((da, ix, ip), shape=(out["n_cell"], out["n_gene"]))
+            obs, var = adata.obs.loc[keep_c].copy(), adata.var.loc[keep_g].copy()
+            if flag_filter_data:
+                obs["n_genes"] = out["n_genes"][keep_c]
+                var["n_cells"] = out["n_cells"][keep_g]
+            if flag_raw_count:
+                obs["n_counts"] = out["n_counts"][keep_c]
+            adata = AnnData(X, obs, var, adata.uns)
+        elif not (isinstance(adata.X, sparse.csr_matrix) and adata.X.dtype == np.float32):
+            adata = AnnData(sparse.csr_matrix((data, indices, indptr), shape=adata.shape), adata.obs, adata.var, adata.uns)
+    except BaseException:
+        ctx.close()
+        raise
+    _device.adopt_context(adata, ctx)      # the matrix is already resident: no upload in preprocess / score_cell
+    return adata
+
+
+def _preprocess_counts_dense(adata, flag_filter_data, flag_raw_count, min_genes, min_cells):
+    X = np.asarray(adata.X)
+    if np.isnan(X.sum()):
+        raise ValueError(_ERR_NAN)
+    if (X < 0).sum() > 0:
+        raise ValueError(_ERR_NEG)
     if flag_filter_data:
-        X = sparse.csr_matrix(adata.X) if sparse.issparse(adata.X) else adata.X
-        n_genes = np.asarray(_nnz_per_row(X)).reshape(-1)
+        n_genes = (X != 0).sum(axis=1)
         keep = n_genes >= min_genes
         adata = adata[keep, :]
         adata.obs["n_genes"] = n_genes[keep]
-        Xc = sparse.csc_matrix(adata.X) if sparse.issparse(adata.X) else adata.X
-        n_cells = np.diff(Xc.indptr) if sparse.issparse(Xc) else (Xc != 0).sum(axis=0)
-        n_cells = np.asarray(n_cells).reshape(-1)
+        n_cells = (np.asarray(adata.X) != 0).sum(axis=0)
         keepg = n_cells >= min_cells
         adata = adata[:, keepg]
         adata.var["n_cells"] = n_cells[keepg]
     if flag_raw_count:
-        counts = np.asarray(adata.X.sum(axis=1)).reshape(-1)
+        counts = np.asarray(adata.X).sum(axis=1)
         keep = counts >= 1
         if not keep.all():
             adata = adata[keep, :]
             counts = counts[keep]
         adata.obs["n_counts"] = counts
-        scale = 1e4 / counts
-        if sparse.issparse(adata.X):
-            X = sparse.csr_matrix(adata.X, dtype=np.float32, copy=True)
-            X.data *= np.repeat(scale, np.diff(X.indptr)).astype(np.float32)
-            X.data = np.log1p(X.data)
-        else:
-            X = np.log1p(np.asarray(adata.X, dtype=np.float32) * scale[:, None].astype(np.float32))
-        adata = AnnData(X, adata.obs, adata.var, adata.uns)
+        scale = (1e4 / counts).astype(np.float32)
+        adata = AnnData(np.log1p(np.asarray(adata.X, dtype=np.float32) * scale[:, None]), adata.obs, adata.var, adata.uns)
     return adata
 
 

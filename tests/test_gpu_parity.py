@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) with the oracle and with the reference's golden
 vectors.  Integer outputs (control indices, rank counts) must be bit-exact; floating-point outputs
 must agree within 1e-5 (BASELINE.json north_star), tolerance written in each test."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -662,3 +664,73 @@ def test_full_size_config4_two_kernels_agree(native_lib):
     rel = np.abs(fx["pval"].values.astype(np.float64) - f64["pval"].values) / f64["pval"].values
     assert rel.max() < 1e-3
     scdrs_b200.clear_device_cache()
+
+
+# ---- the step before the path: load_h5ad's checks, filters and normalisation on the device -----------
+def _raw_counts(n_cell, n_gene, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.gamma(0.5, 1.0, n_gene)
+    q = np.minimum(0.6, 0.08 * q / q.mean())
+    mask = rng.random((n_cell, n_gene)) < q
+    mask[rng.random(n_cell) < 0.05] &= rng.random(n_gene) < 0.1        # some nearly empty cells
+    vals = rng.poisson(2.0, size=(n_cell, n_gene)).astype(np.float32) + 1
+    X = sparse.csr_matrix(np.where(mask, vals, 0).astype(np.float32))
+    X.eliminate_zeros()
+    return X
+
+
+@pytest.mark.parametrize("flt,raw", [(True, True), (True, False), (False, True), (False, False)])
+def test_preprocess_counts_matches_host_restatement(native_lib, flt, raw):
+    """scdrs_preprocess_counts against oracle/h5ad_oracle.py: survivors, entry counts and column ids exact,
+    float32 values within 2e-6 (device log1pf vs numpy); the processed matrix stays resident, so
+    preprocess / score_cell upload nothing."""
+    from oracle import h5ad_oracle
+    from scdrs_b200 import _device, util
+    from scdrs_b200.anndata_lite import AnnData
+
+    X = _raw_counts(1500, 900, 3)
+    obs = pd.DataFrame({"tag": np.arange(1500)}, index=["c%d" % i for i in range(1500)])
+    var = pd.DataFrame({"gtag": np.arange(900)}, index=["g%d" % i for i in range(900)])
+    Y, keep_c, keep_g, n_genes, n_cells, n_counts = h5ad_oracle.preprocess_counts(
+        X, flag_filter_data=flt, flag_raw_count=raw, min_genes=40, min_cells=25)
+    adata = util.preprocess_counts(AnnData(X.copy(), obs, var), flag_filter_data=flt, flag_raw_count=raw,
+                                   min_genes=40, min_cells=25)
+    assert adata.shape == Y.shape
+    assert np.array_equal(adata.obs["tag"].values, np.flatnonzero(keep_c))
+    assert np.array_equal(adata.var["gtag"].values, np.flatnonzero(keep_g))
+    got = adata.X.tocsr()
+    assert np.array_equal(got.indptr, Y.indptr) and np.array_equal(got.indices, Y.indices)
+    assert np.allclose(got.data, Y.data, rtol=2e-6, atol=0)
+    if flt:
+        assert 0 < keep_c.sum() < 1500 and 0 < keep_g.sum() < 900
+        assert np.array_equal(adata.obs["n_genes"].values, n_genes[keep_c])
+        assert np.array_equal(adata.var["n_cells"].values, n_cells[keep_g])
+    if raw:
+        assert np.array_equal(adata.obs["n_counts"].values, n_counts[keep_c])     # integer counts: exact
+    st = _device.get_state(adata)
+    scdrs_mod = __import__("scdrs_b200")
+    scdrs_mod.preprocess(adata)
+    assert st.h2d_bytes == 0, "the matrix was uploaded again"
+    _device.clear_device_cache()
+
+
+def test_preprocess_counts_rejects_nan_and_negative_like_the_reference(native_lib):
+    from scdrs_b200 import util
+    from scdrs_b200.anndata_lite import AnnData
+
+    X = _raw_counts(200, 150, 4)
+    for bad_value, msg in ((np.nan, "NaN"), (-1.0, "negative")):
+        B = X.copy()
+        B.data[17] = bad_value
+        with pytest.raises(ValueError, match=msg):
+            util.preprocess_counts(AnnData(B), flag_filter_data=False, flag_raw_count=False)
+
+
+def test_load_h5ad_toy_file_device_path(native_lib):
+    from scdrs_b200 import util
+
+    adata = util.load_h5ad(os.path.join(helpers.TOY, "toydata_mouse.h5ad"), flag_filter_data=True,
+                           flag_raw_count=True, min_genes=500, min_cells=5)
+    assert "n_genes" in adata.obs and "n_cells" in adata.var and "n_counts" in adata.obs
+    assert np.allclose(np.expm1(adata.X.toarray()).sum(axis=1), 1e4, rtol=1e-4)
+    assert (adata.obs["n_genes"] >= 500).all()

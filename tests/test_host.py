@@ -138,12 +138,23 @@ def test_read_h5ad_toy_file():
     assert adata.obs["cell_type"].iloc[0] == "causal_cell" and adata.var_names[0] == "Pip4k2a"
 
 
-def test_load_h5ad_checks_and_normalisation(tmp_path):
-    adata = util.load_h5ad(os.path.join(helpers.TOY, "toydata_mouse.h5ad"), flag_filter_data=True,
-                           flag_raw_count=True, min_genes=500, min_cells=5)
-    assert "n_genes" in adata.obs and "n_cells" in adata.var and "n_counts" in adata.obs
-    assert np.allclose(np.expm1(adata.X.toarray()).sum(axis=1), 1e4, rtol=1e-4)
-    assert (adata.obs["n_genes"] >= 500).all()
+def test_count_preprocessing_restatement_on_toy_data():
+    """The host restatement of load_h5ad's filters / normalisation (oracle/h5ad_oracle.py), the checker of
+    the device path (tests/test_gpu_parity.py::test_preprocess_counts_*)."""
+    from oracle import h5ad_oracle
+    from scdrs_b200.anndata_lite import read_h5ad
+
+    adata = read_h5ad(os.path.join(helpers.TOY, "toydata_mouse.h5ad"))
+    Y, keep_c, keep_g, n_genes, n_cells, n_counts = h5ad_oracle.preprocess_counts(
+        adata.X, flag_filter_data=True, flag_raw_count=True, min_genes=500, min_cells=5)
+    assert Y.shape == (keep_c.sum(), keep_g.sum()) and Y.dtype == np.float32
+    assert (n_genes[keep_c] >= 500).all() and (n_cells[keep_g] >= 5).all()
+    assert np.allclose(np.expm1(Y.toarray()).sum(axis=1), 1e4, rtol=1e-4)
+    assert np.allclose(n_counts[keep_c], np.asarray(adata.X[keep_c][:, keep_g].sum(axis=1)).reshape(-1))
+    bad = adata.X.copy().astype(np.float32)
+    bad.data[3] = -1.0
+    with pytest.raises(ValueError):
+        h5ad_oracle.preprocess_counts(bad)
 
 
 def test_fdr_bh_matches_textbook():
