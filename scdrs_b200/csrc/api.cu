@@ -132,7 +132,8 @@ static void release_all(scdrs_ctx* c) {
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
-                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr};
+                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr,
+                      &c->fx_xq, &c->fx_meta32};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -291,6 +292,7 @@ int scdrs_set_csr_host(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64
     c->trait_ready = false;
     c->have_stats = false;
     c->fx_stat_key = -1;
+    c->fx_xq_key = -1;
     c->tile_ptr_valid = false;
     c->xsum_valid = false;
     c->covsum_valid = false;
@@ -317,6 +319,7 @@ int scdrs_set_csr_dev(scdrs_ctx* c, int64_t n_cell, int32_t n_gene, const int64_
     c->trait_ready = false;
     c->have_stats = false;
     c->fx_stat_key = -1;
+    c->fx_xq_key = -1;
     c->tile_ptr_valid = false;
     c->xsum_valid = false;
     c->covsum_valid = false;
@@ -364,6 +367,7 @@ int scdrs_set_gene_stats(scdrs_ctx* c, const double* var, const double* var_tech
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     c->have_stats = true;
     c->fx_stat_key = -1;
+    c->fx_xq_key = -1;
     return 0;
 }
 

@@ -87,6 +87,9 @@ struct scdrs_ctx {
     bool w_fx = false;        // the lists currently built are laid out for the fixed-point kernel
     int fx_shift = 0;         // scale = 2^fx_shift
     int fx_n_tile = 1;        // column tiles of the fixed-point scatter
+    bool fx_preq = false;     // binary trait: the scatter reads pre-quantised entries (fx_xq) and 4-byte records
+    int fx_xq_key = -1, fx_xq_shift = 0;   // weight_opt / scale the pre-quantised entries were built for
+    scdrs::DevBuf fx_xq, fx_meta32;
     bool fx_tile0_built = false;
     int fx_stat_key = -1;     // weight_opt the value statistics below were computed for (-1: none)
     double fx_vmax = 0.0, fx_vmean = 0.0;   // max and mean of |x * base_g| over the stored entries

@@ -251,6 +251,7 @@ int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells,
     c->trait_ready = false;
     c->have_stats = false;
     c->fx_stat_key = -1;
+    c->fx_xq_key = -1;
     c->tile_ptr_valid = false;
     c->xsum_valid = false;
     c->covsum_valid = false;

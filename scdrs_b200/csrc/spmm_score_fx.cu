@@ -300,7 +300,8 @@ fx_place_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uint32_t* 
 // GeneInfo for the fixed-point kernel: base = base_g * 2^s, meta = (first block << 8) | blocks
 // (block 0 of the list storage is the all-trash block, a gene's blocks start at 1 + p_ptr / 64)
 __global__ void fx_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, const uint32_t* __restrict__ rounds,
-                               const double* __restrict__ gbase, double scale, GeneInfo* __restrict__ info) {
+                               const double* __restrict__ gbase, double scale, GeneInfo* __restrict__ info,
+                               uint32_t* __restrict__ meta32) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n_gene) {
         GeneInfo gi;
@@ -308,7 +309,18 @@ __global__ void fx_meta_kernel(int n_gene, const uint32_t* __restrict__ p_ptr, c
         gi.meta = (((p_ptr[g] >> 6) + 1u) << 8) | ((rounds[g] + 1u) >> 1);
         gi.pad = 0;
         info[g] = gi;
+        meta32[g] = gi.meta;      // what the pre-quantised path gathers: 4 bytes per gene instead of 16
     }
+}
+
+// Pre-quantised stored entries round(x * base_g * 2^s), once per (matrix, weight_opt, s): binary traits share
+// the scale, so the scatter of every trait reads these integers instead of converting x on the fly, and
+// gathers a 4-byte list location per entry instead of a 16-byte record.
+__global__ void __launch_bounds__(256)
+fx_quantise_kernel(int64_t nnz, const int32_t* __restrict__ indices, const float* __restrict__ data,
+                   const double* __restrict__ gbase, double scale, int32_t* __restrict__ xq) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x)
+        xq[q] = __double2int_rn((double)data[q] * (gbase[indices[q]] * scale));
 }
 
 // Column means of the per-set constants: what the scatter kernel needs to place a cell's reference value
@@ -352,6 +364,18 @@ int fx_prepare(scdrs_ctx* c, bool binary, double gw_absmax) {
     c->w_binary = binary;
     c->w_fx = true;
     c->fx_tile0_built = false;
+    c->fx_preq = false;
+    if (binary && (size_t)c->nnz * sizeof(int32_t) <= ((size_t)48 << 30)) {
+        if (!(c->fx_xq_key == c->fx_stat_key && c->fx_xq_shift == shift && c->fx_xq_key >= 0)) {
+            SCDRS_TRY(c->fx_xq.reserve((size_t)c->nnz * sizeof(int32_t)));
+            fx_quantise_kernel<<<kNumSM * 8, 256, 0, c->stream>>>(c->nnz, c->indices, c->data, c->gbase.as<double>(),
+                                                                 ldexp(1.0, shift), c->fx_xq.as<int32_t>());
+            SCDRS_LAUNCH_CHECK(c);
+            c->fx_xq_key = c->fx_stat_key;
+            c->fx_xq_shift = shift;
+        }
+        c->fx_preq = true;
+    }
     if (c->fx_n_tile == 1) {
         SCDRS_TRY(fx_build_tile(c, 0));
         c->fx_tile0_built = true;
@@ -373,6 +397,7 @@ static int fx_build_tile(scdrs_ctx* c, int tile) {
     SCDRS_TRY(build_gene_lists(c, col0, col1));
     SCDRS_TRY(c->w_code.reserve((size_t)(n_entry > 0 ? n_entry : 1) * sizeof(uint16_t)));
     SCDRS_TRY(c->w_rounds.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
+    SCDRS_TRY(c->fx_meta32.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_col.reserve((size_t)n_slot_max * sizeof(uint16_t)));
     if (!binary) SCDRS_TRY(c->p_val.reserve((size_t)n_slot_max * sizeof(float)));
     static bool attr = false;
@@ -392,7 +417,8 @@ static int fx_build_tile(scdrs_ctx* c, int tile) {
         c->w_code.as<uint16_t>(), c->w_val.as<float>(), c->p_col.as<uint16_t>(), binary ? nullptr : c->p_val.as<float>());
     SCDRS_LAUNCH_CHECK(c);
     fx_meta_kernel<<<(n_gene + 255) / 256, 256, 0, c->stream>>>(n_gene, c->p_ptr.as<uint32_t>(), c->w_rounds.as<uint32_t>(),
-                                                               c->gbase.as<double>(), ldexp(1.0, c->fx_shift), c->p_meta.as<GeneInfo>());
+                                                               c->gbase.as<double>(), ldexp(1.0, c->fx_shift), c->p_meta.as<GeneInfo>(),
+                                                               c->fx_meta32.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
     if (tile == 0) {
         // column means of the per-set constants over the first tile: they place the row reference
@@ -461,10 +487,11 @@ __device__ __forceinline__ uint32_t fx_ldg_pinned(const uint32_t* p) {
 // Per-lane column totals are 32-bit: a flush moves word >> 12 into the total and leaves the low 12 bits
 // in the word (|sum over a row| < 2^18 entries * 2^25 / 2^12 = 2^31), which keeps the kernel at 96
 // registers = 20 warps per SM.
-template <bool WEIGHTED, int D>
+template <bool WEIGHTED, int D, bool PREQ>
 __global__ void __launch_bounds__(kFxWarpsPerBlock * 32, kFxBlocksPerSM)
 spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, int ld, const int64_t* __restrict__ indptr,
                      const int32_t* __restrict__ indices, const float* __restrict__ data,
+                     const int32_t* __restrict__ xq_arr, const uint32_t* __restrict__ meta32,
                      const GeneInfo* __restrict__ ginfo, const uint32_t* __restrict__ p_col32,
                      const float2* __restrict__ p_val2, const double* __restrict__ colscale,
                      double inv_scale, float gwmax, int k, const double* __restrict__ cov_mat,
@@ -515,14 +542,22 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, in
         uint32_t n_left = 0;          // staged items not yet in the slots (fewer than D), carried to the next group
         const int64_t p0 = indptr[row], p1 = indptr[row + 1];
         // chunk pipeline registers: record + value of the current chunk, ids + values of the next two
+        // (pre-quantised path: the value is the integer entry, the record just the 4-byte list location)
+        auto load_val = [&](int64_t q) -> float {
+            return PREQ ? __int_as_float(__ldg(xq_arr + q)) : __ldg(data + q);
+        };
+        auto load_rec = [&](int g) -> int4 {
+            if (PREQ) return make_int4(0, 0, (int)__ldg(meta32 + g), 0);
+            return __ldg(reinterpret_cast<const int4*>(ginfo + g));
+        };
         int4 gi0 = make_int4(0, 0, 0, 0);
         float dat0 = 0.f, dat1 = 0.f, dat2 = 0.f;
         int idx1 = -1, idx2 = -1;
         {
             int idx0 = -1;
-            if (p0 + lane < p1) { idx0 = __ldg(indices + p0 + lane); dat0 = __ldg(data + p0 + lane); }
-            if (p0 + 32 + lane < p1) { idx1 = __ldg(indices + p0 + 32 + lane); dat1 = __ldg(data + p0 + 32 + lane); }
-            if (idx0 >= 0) gi0 = __ldg(reinterpret_cast<const int4*>(ginfo + idx0));
+            if (p0 + lane < p1) { idx0 = __ldg(indices + p0 + lane); dat0 = load_val(p0 + lane); }
+            if (p0 + 32 + lane < p1) { idx1 = __ldg(indices + p0 + 32 + lane); dat1 = load_val(p0 + 32 + lane); }
+            if (idx0 >= 0) gi0 = load_rec(idx0);
         }
         for (int64_t base = p0;; base += 32) {
             const bool done = base >= p1;
@@ -551,7 +586,12 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, in
             const uint32_t meta = (uint32_t)gi0.z, nblk = done ? 0u : (meta & 255u), blk0 = meta >> 8;
             uint32_t qb = 0;
             int xq = 0;      // binary: the quantised entry; weighted: the bits of the scaled entry (float)
-            if (nblk) {
+            if (PREQ) {
+                if (nblk) {
+                    xq = __float_as_int(dat0);
+                    qb = (uint32_t)(xq < 0 ? -xq : xq);
+                }
+            } else if (nblk) {
                 const double vs = (double)dat0 * __hiloint2double(gi0.y, gi0.x);
                 if (WEIGHTED) {
                     const float vf = (float)vs;
@@ -584,10 +624,10 @@ spmm_score_fx_kernel(int64_t n_cell, int ncol, int cov_stride, int write_ref, in
 
             // stage the loads of the chunks after this one
             int4 gi1 = make_int4(0, 0, 0, 0);
-            if (idx1 >= 0) gi1 = __ldg(reinterpret_cast<const int4*>(ginfo + idx1));
+            if (idx1 >= 0) gi1 = load_rec(idx1);
             idx2 = -1;
             dat2 = 0.f;
-            if (base + 64 + lane < p1) { idx2 = __ldg(indices + base + 64 + lane); dat2 = __ldg(data + base + 64 + lane); }
+            if (base + 64 + lane < p1) { idx2 = __ldg(indices + base + 64 + lane); dat2 = load_val(base + 64 + lane); }
 
             for (uint32_t pg = 0;; pg += 4) {
                 // compact the items of passes pg .. pg+3 into shared memory
@@ -700,8 +740,9 @@ int fx_spmm(scdrs_ctx* c) {
     const size_t smem = (size_t)kFxWarpBytes * wpb;
     static bool attr_set = false;
     if (!attr_set) {
-        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_fx_kernel<true, kFxDepthWeighted>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_fx_kernel<false, kFxDepthBinary>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_fx_kernel<true, kFxDepthWeighted, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_fx_kernel<false, kFxDepthBinary, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCDRS_CUDA(cudaFuncSetAttribute(spmm_score_fx_kernel<false, kFxDepthBinary, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int64_t grid = (int64_t)kNumSM * per_sm;
@@ -717,16 +758,23 @@ int fx_spmm(scdrs_ctx* c) {
         if (!(tile == 0 && c->fx_tile0_built)) SCDRS_TRY(fx_build_tile(c, tile));
         const int col0 = tile * kFxMaxCol;
         const int ncol_t = (col0 + kFxMaxCol < c->ncol ? col0 + kFxMaxCol : c->ncol) - col0;
-        if (c->w_binary)
-            spmm_score_fx_kernel<false, kFxDepthBinary><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+        if (c->w_binary && c->fx_preq)
+            spmm_score_fx_kernel<false, kFxDepthBinary, true><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
                 c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
+                c->fx_xq.as<int32_t>(), c->fx_meta32.as<uint32_t>(), c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(),
+                nullptr, c->colscale.as<double>() + col0, inv_scale, c->fx_gwmax, c->k, c->cov_mat.as<double>(),
+                c->covM.as<double>() + col0, c->covm.as<double>() + col0, c->fx_scal.as<double>(),
+                c->dev_mat.as<float>() + col0, c->row_ref.as<double>(), c->fx_rowctr.as<unsigned long long>() + tile);
+        else if (c->w_binary)
+            spmm_score_fx_kernel<false, kFxDepthBinary, false><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+                c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data, nullptr, nullptr,
                 c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), nullptr, c->colscale.as<double>() + col0, inv_scale,
                 c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0, c->covm.as<double>() + col0,
                 c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0, c->row_ref.as<double>(),
                 c->fx_rowctr.as<unsigned long long>() + tile);
         else
-            spmm_score_fx_kernel<true, kFxDepthWeighted><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
-                c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data,
+            spmm_score_fx_kernel<true, kFxDepthWeighted, false><<<(unsigned)grid, wpb * 32, smem, c->stream>>>(
+                c->n_cell, ncol_t, c->ncol, tile == 0 ? 1 : 0, c->ld, c->indptr, c->indices, c->data, nullptr, nullptr,
                 c->p_meta.as<GeneInfo>(), c->p_col.as<uint32_t>(), c->p_val.as<float2>(), c->colscale.as<double>() + col0,
                 inv_scale, c->fx_gwmax, c->k, c->cov_mat.as<double>(), c->covM.as<double>() + col0,
                 c->covm.as<double>() + col0, c->fx_scal.as<double>(), c->dev_mat.as<float>() + col0,
