@@ -158,6 +158,30 @@ int scdrs_gene_cell_stats(scdrs_ctx* ctx, int32_t transform, const double* cell_
  * with scipy's float32 operation order; xtc[n_gene x k] f64 = (C^T X)^T accumulated in cell order. */
 int scdrs_gene_mean_xtc(scdrs_ctx* ctx, int32_t k, const double* cov_mat, float* gene_mean, double* xtc);
 
+/* ---- downstream analyses of one trait's score matrix -------------
+ * scdrs.method.downstream_corr_analysis / downstream_group_analysis / test_gearysc / gearys_c
+ * (scdrs/method.py:712-865, 915-1085).  The caller uploads the trait's scores once:
+ * mat[n_cell x ncol] row-major host memory, column 0 = norm_score, columns 1.. = ctrl_norm_score_i
+ * (is_f32: float32 frame, else float64); the cells may be any subset / order the caller aligned. */
+int scdrs_ds_set_scores(scdrs_ctx* ctx, int64_t n_cell, int32_t ncol, const void* mat, int32_t is_f32);
+/* np.corrcoef(var, score column)[0, 1] for every variable and column (scdrs/method.py:853-857):
+ * vars[n_var x n_cell] host f64 -> corr[n_var x ncol] host f64. */
+int scdrs_ds_corr(scdrs_ctx* ctx, int32_t n_var, const double* vars, double* corr);
+/* Per cell group (order[n_cell]: cells sorted by group, the caller's order inside a group;
+ * grp_ptr[n_group + 1]) and per score column, all outputs host f64 [n_group x ncol]:
+ *   quantile (NULL = skip): np.quantile(column of the group, q), q_lo[g] / q_gamma[g] = numpy's lower
+ *     index and interpolation weight for a group of that size (scdrs/method.py:797-801);
+ *   geary_mode 0: nothing more.  1: every column is first given the distribution of column 0 inside
+ *     the group by ordinal rank (control_distribution_match, scdrs/method.py:976-990); 2: columns as
+ *     they are.  Then geary_total = sum over the stored within-group edges (p, q) of w (x_p - x_q)^2
+ *     and geary_denom = sum_p (x_p - mean)^2 (scdrs/method.py:1070-1082; C = (N-1) total / (2 W denom)).
+ *     Graph: CSR over cells in group order, g_nbr = neighbour positions in group order, only edges
+ *     inside a group (g_indptr[n_cell + 1] i64, g_nbr i32, g_w f64). */
+int scdrs_ds_group_stats(scdrs_ctx* ctx, int32_t n_group, const int64_t* order, const int64_t* grp_ptr,
+                         const int32_t* q_lo, const double* q_gamma, double* quantile,
+                         int32_t geary_mode, const int64_t* g_indptr, const int32_t* g_nbr,
+                         const double* g_w, double* geary_total, double* geary_denom);
+
 /* ---- host code: the random draws of _select_ctrl_geneset (scdrs/method.py:276, 295-307) --------
  * numpy-legacy MT19937 seeded with `seed`, bins visited in the given order; for every bin b with
  * bin_ntrait[b] > 0 and every control set i: permutation(len(bin b))[:bin_ntrait[b]] indexes

@@ -58,6 +58,11 @@ SIGNATURES = {
     "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_gene_mean_xtc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_ds_set_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
+    "scdrs_ds_corr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "scdrs_ds_group_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p]),
     "scdrs_write_score_gz": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
@@ -306,6 +311,43 @@ class Context:
         check(self._L.scdrs_gene_cell_stats(self._h, int(transform), ptr(w), int(bool(center)), float(denom),
                                             ptr(gs), ptr(gq), ptr(cs), ptr(cq)))
         return gs, gq, cs, cq
+
+    # ---- downstream analyses of one trait's score matrix (include/scdrs_b200.h) ----
+    def ds_set_scores(self, mat):
+        """mat[n_cell x ncol] float32 or float64 (column 0 = norm_score, then the control columns)."""
+        mat = np.asarray(mat)
+        f32 = mat.dtype == np.float32
+        mat = as_c(mat, np.float32 if f32 else np.float64)
+        assert mat.ndim == 2
+        check(self._L.scdrs_ds_set_scores(self._h, mat.shape[0], mat.shape[1], ptr(mat), int(f32)))
+        self.ds_shape = mat.shape
+
+    def ds_corr(self, variables):
+        """variables[n_var x n_cell] -> Pearson correlation with every score column [n_var x ncol]."""
+        v = as_c(np.atleast_2d(variables), np.float64)
+        assert v.shape[1] == self.ds_shape[0]
+        out = np.empty((v.shape[0], self.ds_shape[1]), np.float64)
+        check(self._L.scdrs_ds_corr(self._h, v.shape[0], ptr(v), ptr(out)))
+        return out
+
+    def ds_group_stats(self, order, grp_ptr, q_lo=None, q_gamma=None, geary_mode=0, graph=None):
+        """(quantile, geary_total, geary_denom), each [n_group x ncol] or None.  graph = (indptr, nbr, w) of
+        the within-group edges with cells in group order."""
+        order, grp_ptr = as_c(order, np.int64), as_c(grp_ptr, np.int64)
+        n_group = grp_ptr.shape[0] - 1
+        shape = (n_group, self.ds_shape[1])
+        quant = None
+        if q_lo is not None:
+            q_lo, q_gamma = as_c(q_lo, np.int32), as_c(q_gamma, np.float64)
+            quant = np.empty(shape, np.float64)
+        total = denom = gi = gn = gw = None
+        if geary_mode:
+            gi, gn, gw = as_c(graph[0], np.int64), as_c(graph[1], np.int32), as_c(graph[2], np.float64)
+            total, denom = np.empty(shape, np.float64), np.empty(shape, np.float64)
+        check(self._L.scdrs_ds_group_stats(self._h, n_group, ptr(order), ptr(grp_ptr), ptr(q_lo), ptr(q_gamma),
+                                           ptr(quant), int(geary_mode), ptr(gi), ptr(gn), ptr(gw), ptr(total),
+                                           ptr(denom)))
+        return quant, total, denom
 
 
 def select_ctrl(seed, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s):

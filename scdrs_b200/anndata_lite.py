@@ -14,7 +14,7 @@ from . import h5lite
 
 
 class AnnData:
-    def __init__(self, X, obs=None, var=None, uns=None):
+    def __init__(self, X, obs=None, var=None, uns=None, obsp=None):
         if not (sparse.issparse(X) or isinstance(X, np.ndarray)):
             X = np.asarray(X)
         n_obs, n_var = X.shape
@@ -23,6 +23,7 @@ class AnnData:
         self.var = pd.DataFrame(index=pd.RangeIndex(n_var).astype(str)) if var is None else var
         assert len(self.obs) == n_obs and len(self.var) == n_var, "obs/var do not match X"
         self.uns = {} if uns is None else uns
+        self.obsp = {} if obsp is None else obsp      # cell x cell matrices ("connectivities")
 
     @property
     def X(self):
@@ -56,17 +57,29 @@ class AnnData:
     def copy(self):
         import copy as _copy
 
-        return AnnData(self._X.copy(), self.obs.copy(), self.var.copy(), _copy.deepcopy(self.uns))
+        return AnnData(self._X.copy(), self.obs.copy(), self.var.copy(), _copy.deepcopy(self.uns),
+                       {k: v.copy() for k, v in self.obsp.items()})
 
     def __getitem__(self, key):
-        """Row/column subsetting by boolean masks, integer arrays or slices."""
+        """Row/column subsetting by boolean masks, integer arrays, slices or obs / var names."""
         if not isinstance(key, tuple):
             key = (key, slice(None))
         r, c = key
-        r = np.asarray(r) if not isinstance(r, slice) else r
-        c = np.asarray(c) if not isinstance(c, slice) else c
+
+        def positions(k, index):
+            if isinstance(k, slice):
+                return k
+            k = np.asarray(k)
+            if k.dtype.kind in "OUT" or (k.dtype.kind not in "biu"):      # names
+                pos = index.get_indexer(k)
+                assert (pos >= 0).all(), "unknown names in index"
+                return pos
+            return k
+
+        r, c = positions(r, self.obs.index), positions(c, self.var.index)
         X = self._X[r, :][:, c]
-        return AnnData(X, self.obs.iloc[r].copy(), self.var.iloc[c].copy(), dict(self.uns))
+        obsp = {k: v[r][:, r] for k, v in self.obsp.items()}
+        return AnnData(X, self.obs.iloc[r].copy(), self.var.iloc[c].copy(), dict(self.uns), obsp)
 
     def __repr__(self):
         return "AnnData-lite object with n_obs x n_vars = %d x %d" % self.shape

@@ -133,7 +133,8 @@ static void release_all(scdrs_ctx* c) {
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
                       &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr,
-                      &c->fx_xq, &c->fx_meta32};
+                      &c->fx_xq, &c->fx_meta32, &c->ds_S, &c->ds_tmp, &c->ds_pos, &c->ds_M, &c->ds_keys,
+                      &c->ds_vals, &c->ds_off, &c->ds_ref, &c->ds_chunk, &c->ds_part};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -612,6 +613,80 @@ int scdrs_gene_mean_xtc(scdrs_ctx* c, int32_t k, const double* cov_mat, float* g
     if (rc == 0 && k > 0) rc = d2h(c, xtc, d_xtc, (size_t)g * k * sizeof(double));
     if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("stream sync failed"); rc = 1; }
     d_cov.release();
+    return rc;
+}
+
+// ---- downstream analyses of one trait's score matrix (downstream.cu) ------------------------------
+int scdrs_ds_set_scores(scdrs_ctx* c, int64_t n_cell, int32_t ncol, const void* mat, int32_t is_f32) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(mat != nullptr && n_cell > 0 && ncol > 0, "empty score matrix");
+    const size_t m = (size_t)n_cell * ncol;
+    c->ds_n = 0;
+    SCDRS_TRY(c->ds_S.reserve(m * sizeof(double)));
+    if (is_f32) {
+        SCDRS_TRY(h2d_big(c, c->ds_M, mat, m * sizeof(float)));
+        SCDRS_TRY(ds_widen(c, (int64_t)m, c->ds_M.as<float>(), c->ds_S.as<double>()));
+    } else {
+        SCDRS_TRY(h2d_big(c, c->ds_S, mat, m * sizeof(double)));
+    }
+    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    c->ds_n = n_cell;
+    c->ds_ncol = ncol;
+    c->ds_f32 = is_f32 != 0;
+    return 0;
+}
+
+int scdrs_ds_corr(scdrs_ctx* c, int32_t n_var, const double* vars, double* corr) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->ds_n > 0, "no score matrix set (scdrs_ds_set_scores)");
+    SCDRS_CHECK(n_var > 0 && vars != nullptr && corr != nullptr, "null pointer");
+    DevBuf d_vars, d_corr;
+    int rc = h2d(c, d_vars, vars, (size_t)n_var * c->ds_n * sizeof(double)) ||
+             d_corr.reserve((size_t)n_var * c->ds_ncol * sizeof(double));
+    if (rc == 0) rc = ds_corr(c, n_var, d_vars.as<double>(), d_corr.as<double>());
+    if (rc == 0) rc = d2h(c, corr, d_corr.p, (size_t)n_var * c->ds_ncol * sizeof(double));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    d_vars.release();
+    d_corr.release();
+    return rc;
+}
+
+int scdrs_ds_group_stats(scdrs_ctx* c, int32_t n_group, const int64_t* order, const int64_t* grp_ptr,
+                         const int32_t* q_lo, const double* q_gamma, double* quantile, int32_t geary_mode,
+                         const int64_t* g_indptr, const int32_t* g_nbr, const double* g_w, double* geary_total,
+                         double* geary_denom) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->ds_n > 0, "no score matrix set (scdrs_ds_set_scores)");
+    SCDRS_CHECK(n_group > 0 && order != nullptr && grp_ptr != nullptr, "null pointer");
+    SCDRS_CHECK(geary_mode >= 0 && geary_mode <= 2, "geary_mode must be 0, 1 or 2");
+    SCDRS_CHECK(quantile == nullptr || (q_lo != nullptr && q_gamma != nullptr), "quantile positions missing");
+    SCDRS_CHECK(geary_mode == 0 || (g_indptr && geary_total && geary_denom), "graph or outputs missing");
+    const int64_t n = c->ds_n;
+    SCDRS_CHECK(grp_ptr[0] == 0 && grp_ptr[n_group] == n, "grp_ptr must cover all cells");
+    for (int g = 0; g < n_group; ++g) SCDRS_CHECK(grp_ptr[g] <= grp_ptr[g + 1], "grp_ptr must not decrease");
+    const size_t gm = (size_t)n_group * c->ds_ncol * sizeof(double);
+    DevBuf d_order, d_gptr, d_qlo, d_qg, d_gi, d_gn, d_gw, d_out;
+    int rc = h2d(c, d_order, order, (size_t)n * 8) || h2d(c, d_gptr, grp_ptr, (size_t)(n_group + 1) * 8) ||
+             d_out.reserve(3 * gm);
+    if (rc == 0 && quantile) rc = h2d(c, d_qlo, q_lo, (size_t)n_group * 4) || h2d(c, d_qg, q_gamma, (size_t)n_group * 8);
+    if (rc == 0 && geary_mode) {
+        const int64_t ne = g_indptr[n];
+        SCDRS_CHECK(ne == 0 || (g_nbr != nullptr && g_w != nullptr), "graph arrays missing");
+        rc = h2d(c, d_gi, g_indptr, (size_t)(n + 1) * 8) || d_gn.reserve(8) || d_gw.reserve(8) ||
+             h2d(c, d_gn, g_nbr, (size_t)ne * 4) || h2d(c, d_gw, g_w, (size_t)ne * 8);
+    }
+    double* d_quant = d_out.as<double>();
+    double* d_total = d_quant + (size_t)n_group * c->ds_ncol;
+    double* d_denom = d_total + (size_t)n_group * c->ds_ncol;
+    if (rc == 0)
+        rc = ds_group_stats(c, n_group, grp_ptr, d_order.as<int64_t>(), d_gptr.as<int64_t>(), d_qlo.as<int32_t>(),
+                            d_qg.as<double>(), quantile ? d_quant : nullptr, geary_mode, d_gi.as<int64_t>(),
+                            d_gn.as<int32_t>(), d_gw.as<double>(), d_total, d_denom);
+    if (rc == 0 && quantile) rc = d2h(c, quantile, d_quant, gm);
+    if (rc == 0 && geary_mode) rc = d2h(c, geary_total, d_total, gm) || d2h(c, geary_denom, d_denom, gm);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    DevBuf* tmp[] = {&d_order, &d_gptr, &d_qlo, &d_qg, &d_gi, &d_gn, &d_gw, &d_out};
+    for (DevBuf* b : tmp) b->release();
     return rc;
 }
 

@@ -75,6 +75,12 @@ struct scdrs_ctx {
     int32_t k = 0;  // number of covariates (0 = normal mode)
     scdrs::DevBuf cov_mat, cov_beta, gene_mean;
 
+    // downstream analyses (downstream.cu): the score matrix of one trait, [ds_n x ds_ncol] fp64 row-major
+    scdrs::DevBuf ds_S, ds_tmp, ds_pos, ds_M, ds_keys, ds_vals, ds_off, ds_ref, ds_chunk, ds_part;
+    int64_t ds_n = 0;
+    int32_t ds_ncol = 0;
+    bool ds_f32 = false;      // the caller's frame was float32 (numpy interpolates quantiles of float32 differently)
+
     // per-trait state
     int32_t n_ctrl = 0, n_s = 0, n_sc = 0, ncol = 0, ld = 0;  // n_s: trait set size, n_sc: control set size
     bool trait_ready = false;
@@ -170,6 +176,14 @@ int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells,
                       int* has_nan, int* has_negative, int64_t* n_cell_out, int32_t* n_gene_out, int64_t* nnz_out,
                       uint8_t* h_keep_cell, uint8_t* h_keep_gene, int32_t* h_n_genes, int32_t* h_n_cells,
                       float* h_n_counts);
+
+// ---- downstream.cu ----------------------------------------------------------------------------
+int ds_widen(scdrs_ctx* c, int64_t m, const float* dev_in, double* dev_out);
+int ds_corr(scdrs_ctx* c, int n_var, const double* dev_vars, double* dev_corr);
+int ds_group_stats(scdrs_ctx* c, int n_group, const int64_t* h_gptr, const int64_t* d_order, const int64_t* d_gptr,
+                   const int32_t* d_qlo, const double* d_qgamma, double* d_quant, int geary_mode,
+                   const int64_t* d_gindptr, const int32_t* d_gnbr, const double* d_gw, double* d_total,
+                   double* d_denom);
 
 // ---- scan (empi_null.cu) --------------------------------------------------------------------
 int exclusive_scan_u32(scdrs_ctx* c, const uint32_t* in, uint32_t* out, int64_t n);

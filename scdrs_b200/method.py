@@ -454,3 +454,17 @@ def score_traits(
         drain(0)
     np.random.seed(random_seed)
     return results if on_result is None else traits
+
+
+# ----------------------------------------------------------------------------------------------
+# downstream analyses (scdrs/method.py:712-1166): implemented in scdrs_b200/downstream.py
+# ----------------------------------------------------------------------------------------------
+from .downstream import (  # noqa: E402,F401
+    _pearson_corr,
+    _pearson_corr_sparse,
+    downstream_corr_analysis,
+    downstream_gene_analysis,
+    downstream_group_analysis,
+    gearys_c,
+    test_gearysc,
+)

@@ -2,6 +2,8 @@
 the reference's golden score files for the toy data, its own known-answer tests, and outputs of the
 unmodified reference sources committed under tests/golden/ (plus a live comparison when
 /root/reference is present)."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -102,3 +104,71 @@ def test_oracle_matches_live_reference():
     ref = method.score_cell(adata, genes, gene_weight=w, n_ctrl=40, return_ctrl_norm_score=True)
     mine = orc.score_cell(adata, genes, gene_weight=w, n_ctrl=40, return_ctrl_norm_score=True)
     assert np.array_equal(ref.values, mine.values)
+
+
+# ---- downstream analyses: oracle/downstream_oracle.py --------------------
+from oracle import downstream_oracle as dso  # noqa: E402
+
+
+def _toy_downstream():
+    adata, _, _, ref, _ = helpers.load_toy()
+    full = ref["REF_COV_FULL"]
+    ctrl = full[[c for c in full.columns if c.startswith("ctrl_norm_score")]].values
+    pre = os.path.join(helpers.TOY, "toydata_gs_mouse.ref_Ctrl20_CovConstCovariate.")
+    gold = {k: pd.read_csv(pre + k, sep="\t", index_col=0) for k in ("scdrs_cell_corr", "scdrs_gene", "scdrs_group.cell_type")}
+    return adata, full, ctrl, gold
+
+
+def test_downstream_oracle_reproduces_reference_golden_files():
+    """The reference's own outputs for the toy data (scdrs/data/*.scdrs_*): every column that does not need
+    scanpy's neighbour graph."""
+    adata, full, ctrl, gold = _toy_downstream()
+    assert list(full.index) == list(adata.obs_names)
+    vcols = list(gold["scdrs_cell_corr"].index)
+    got = dso.corr_analysis([adata.obs[v].values.astype(np.float64) for v in vcols], full["norm_score"].values, ctrl)
+    np.testing.assert_allclose(got, gold["scdrs_cell_corr"].values, rtol=2e-6)
+    gene = dso.gene_analysis(adata.X, adata.var_names, full["norm_score"].values)
+    g = gold["scdrs_gene"]
+    np.testing.assert_allclose(gene.loc[g.index, "CORR"].values, g["CORR"].values, rtol=1e-5, atol=1e-7)
+    # ranks differ only inside runs of tied correlations (the reference sorts with an unstable quicksort)
+    differ = gene.loc[g.index, "RANK"].values != g["RANK"].values
+    assert differ.mean() < 0.01
+    np.testing.assert_allclose(gene["CORR"].values[g["RANK"].values[differ].astype(int)], g["CORR"].values[differ], rtol=1e-5, atol=1e-7)
+    grp = dso.group_analysis(None, adata.obs["cell_type"].values, full["norm_score"].values, ctrl, full["pval"].values)
+    gg = gold["scdrs_group.cell_type"]
+    for col in ["n_cell", "n_ctrl", "assoc_mcp", "assoc_mcz", "n_fdr_0.05", "n_fdr_0.1", "n_fdr_0.2"]:
+        np.testing.assert_allclose(grp.loc[gg.index, col].values.astype(float), gg[col].values, rtol=2e-6, err_msg=col)
+
+
+def test_downstream_oracle_matches_committed_reference_outputs():
+    adata, df, ref = helpers.load_downstream_case()
+    order = sorted(adata.obs_names)
+    sub = adata[order]
+    dfo = df.loc[order]
+    ctrl = dfo[[c for c in df.columns if c.startswith("ctrl_norm_score")]].values
+    G = sub.obsp["connectivities"]
+    grp = dso.group_analysis(G, sub.obs["grp"].values, dfo["norm_score"].values, ctrl, dfo["pval"].values)
+    np.testing.assert_allclose(grp.loc[ref["group"].index].values.astype(float), ref["group"].values, rtol=1e-5, equal_nan=True)
+    rls = dso.test_gearysc(G, sub.obs["grp"].values, dfo["norm_score"].values, ctrl)
+    np.testing.assert_allclose(rls.loc[ref["rls"].index].values, ref["rls"].values, rtol=1e-9, equal_nan=True)
+    rls = dso.test_gearysc(G, sub.obs["grp"].values, dfo["norm_score"].values, ctrl, opt="control")
+    np.testing.assert_allclose(rls.loc[ref["rls"].index].values, ref["rls_ctrl"].values, rtol=1e-9, equal_nan=True)
+    corr = dso.corr_analysis([sub.obs["v1"].values, sub.obs["v2"].values], dfo["norm_score"].values, ctrl)
+    np.testing.assert_allclose(corr, ref["corr"], rtol=1e-6)
+    gene = dso.gene_analysis(sub.X, adata.var_names, dfo["norm_score"].values)
+    np.testing.assert_allclose(gene.loc[ref["gene"].index].values, ref["gene"].values, rtol=1e-5, atol=1e-7)
+    gc = dso.gearys_c(adata.obsp["connectivities"], df["norm_score"].values)
+    assert abs(gc - ref["gearys_c"]) < 1e-12
+
+
+def test_gearys_c_oracle_against_the_double_loop():
+    """tests/test_method_downstream.py:14-24 of the reference: the naive O(N^2) definition."""
+    adata, df = helpers.make_downstream_inputs(60, 2, 3, k=5, seed=3)
+    W = adata.obsp["connectivities"].toarray().astype(np.float64)
+    x = np.arange(60, dtype=np.float64)
+    c = 0.0
+    for i in range(60):
+        for j in range(60):
+            c += W[i, j] * (x[i] - x[j]) ** 2
+    c = c * 59 / 2 / W.sum() / np.sum((x - x.mean()) ** 2)
+    assert np.allclose(dso.gearys_c(adata.obsp["connectivities"], x), c)
