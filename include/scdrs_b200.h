@@ -160,10 +160,14 @@ int scdrs_gene_mean_xtc(scdrs_ctx* ctx, int32_t k, const double* cov_mat, float*
 
 /* ---- downstream analyses of one trait's score matrix -------------
  * scdrs.method.downstream_corr_analysis / downstream_group_analysis / test_gearysc / gearys_c
- * (scdrs/method.py:712-865, 915-1085).  The caller uploads the trait's scores once:
- * mat[n_cell x ncol] row-major host memory, column 0 = norm_score, columns 1.. = ctrl_norm_score_i
- * (is_f32: float32 frame, else float64); the cells may be any subset / order the caller aligned. */
-int scdrs_ds_set_scores(scdrs_ctx* ctx, int64_t n_cell, int32_t ncol, const void* mat, int32_t is_f32);
+ * (scdrs/method.py:712-865, 915-1085).  The caller uploads the trait's scores once, straight from the
+ * memory of its score frame: `frame` holds n_elem values (float32 when is_f32, else float64); score
+ * (r, j) is frame[r * row_stride + cols[j] * col_stride] -- col_stride 1 for a row-major frame,
+ * row_stride 1 for a column-major one (what pandas usually holds).  cols[0] = the norm_score column,
+ * cols[1..] = the ctrl_norm_score_i columns.  On the device the scores become fp64 [n_cell x ncol]; the
+ * rows may be any subset / order of the cells, the other calls refer to them by row number. */
+int scdrs_ds_set_scores(scdrs_ctx* ctx, int64_t n_cell, int32_t ncol, const void* frame, int32_t is_f32,
+                        int64_t n_elem, int64_t row_stride, int64_t col_stride, const int32_t* cols);
 /* np.corrcoef(var, score column)[0, 1] for every variable and column (scdrs/method.py:853-857):
  * vars[n_var x n_cell] host f64 -> corr[n_var x ncol] host f64. */
 int scdrs_ds_corr(scdrs_ctx* ctx, int32_t n_var, const double* vars, double* corr);

@@ -58,7 +58,8 @@ SIGNATURES = {
     "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_gene_mean_xtc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "scdrs_ds_set_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
+    "scdrs_ds_set_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                      C.c_int64, C.c_void_p]),
     "scdrs_ds_corr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scdrs_ds_group_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -313,14 +314,21 @@ class Context:
         return gs, gq, cs, cq
 
     # ---- downstream analyses of one trait's score matrix (include/scdrs_b200.h) ----
-    def ds_set_scores(self, mat):
-        """mat[n_cell x ncol] float32 or float64 (column 0 = norm_score, then the control columns)."""
-        mat = np.asarray(mat)
-        f32 = mat.dtype == np.float32
-        mat = as_c(mat, np.float32 if f32 else np.float64)
-        assert mat.ndim == 2
-        check(self._L.scdrs_ds_set_scores(self._h, mat.shape[0], mat.shape[1], ptr(mat), int(f32)))
-        self.ds_shape = mat.shape
+    def ds_set_scores(self, frame, cols=None):
+        """frame[n_cell x m] float32 or float64, C- or F-contiguous (uploaded as it lies in memory); cols: the
+        columns that make up the score matrix (norm_score first, then the control columns; default all)."""
+        frame = np.asarray(frame)
+        assert frame.ndim == 2
+        if frame.dtype not in (np.float32, np.float64):
+            frame = frame.astype(np.float64)
+        if not (frame.flags["C_CONTIGUOUS"] or frame.flags["F_CONTIGUOUS"]):
+            frame = np.ascontiguousarray(frame)
+        n, m = frame.shape
+        rs, cs = (m, 1) if frame.flags["C_CONTIGUOUS"] else (1, n)
+        cols = as_c(np.arange(m) if cols is None else cols, np.int32)
+        check(self._L.scdrs_ds_set_scores(self._h, n, cols.shape[0], frame.ctypes.data, int(frame.dtype == np.float32),
+                                          n * m, rs, cs, ptr(cols)))
+        self.ds_shape = (n, cols.shape[0])
 
     def ds_corr(self, variables):
         """variables[n_var x n_cell] -> Pearson correlation with every score column [n_var x ncol]."""

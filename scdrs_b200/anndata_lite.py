@@ -109,15 +109,21 @@ def _read_frame(g):
     return df
 
 
-def read_h5ad(path):
-    """Read ``X`` (csr/csc/dense), ``obs`` and ``var`` of an ``.h5ad`` file."""
-    f = h5lite.File(path)
-    x = f["X"]
+def _read_matrix(x):
     if isinstance(x, h5lite.Group):
         enc = str(x.attrs.get("encoding-type", x.attrs.get("h5sparse_format", "csr_matrix")))
         shape = tuple(int(s) for s in x.attrs.get("shape", x.attrs.get("h5sparse_shape")))
         parts = (x["data"].read(), x["indices"].read(), x["indptr"].read())
-        X = (sparse.csc_matrix if enc.startswith("csc") else sparse.csr_matrix)(parts, shape=shape)
-    else:
-        X = x.read()
-    return AnnData(X, _read_frame(f["obs"]), _read_frame(f["var"]))
+        return (sparse.csc_matrix if enc.startswith("csc") else sparse.csr_matrix)(parts, shape=shape)
+    return x.read()
+
+
+def read_h5ad(path):
+    """Read ``X`` (csr/csc/dense), ``obs``, ``var`` and the ``obsp`` matrices (the neighbour graph
+    ``connectivities`` the downstream analyses use) of an ``.h5ad`` file."""
+    f = h5lite.File(path)
+    obsp = {}
+    if "obsp" in f and isinstance(f["obsp"], h5lite.Group):
+        for key in f["obsp"].keys():
+            obsp[str(key)] = _read_matrix(f["obsp"][key])
+    return AnnData(_read_matrix(f["X"]), _read_frame(f["obs"]), _read_frame(f["var"]), obsp=obsp)

@@ -1,9 +1,10 @@
-"""``scdrs compute-score`` (drop-in for bin/scdrs:25-304 of the reference).
+"""``scdrs compute-score`` and ``scdrs perform-downstream`` (drop-ins for bin/scdrs:25-304 and :558-816 of
+the reference).
 
 python-fire is not installed here, so the flag conventions it gives the reference's CLI are
 restated: ``compute-score`` / ``compute_score``, ``--h5ad-file`` / ``--h5ad_file``,
-``--flag True`` / ``--flag=False``.  Only the ``compute-score`` sub-command is on the hot path;
-``munge-gs`` and ``perform-downstream`` are outside this repository's scope.
+``--flag True`` / ``--flag=False``.  ``compute-score`` is the hot path, ``perform-downstream`` the step right
+after it; ``munge-gs`` is outside this repository's scope.
 """
 import os
 import sys
@@ -21,6 +22,15 @@ _SIGNATURE = [
     ("flag_raw_count", bool, True), ("n_ctrl", int, 1000), ("min_genes", int, 250), ("min_cells", int, 50),
     ("flag_return_ctrl_raw_score", bool, False), ("flag_return_ctrl_norm_score", bool, True),
 ]
+
+
+_SIGNATURE_DOWNSTREAM = [
+    ("h5ad_file", str, None), ("score_file", str, None), ("out_folder", str, None), ("group_analysis", str, None),
+    ("corr_analysis", str, None), ("gene_analysis", str, None), ("flag_filter_data", bool, True),
+    ("flag_raw_count", bool, True), ("min_genes", int, 250), ("min_cells", int, 50), ("knn_n_neighbors", int, 15),
+    ("knn_n_pcs", int, 20),
+]
+_SIGNATURES = {"compute_score": _SIGNATURE, "perform_downstream": _SIGNATURE_DOWNSTREAM}
 
 
 def get_cli_head():
@@ -47,7 +57,7 @@ def parse_cli(argv):
     if not argv:
         raise SystemExit("usage: scdrs compute-score --h5ad-file ... --gs-file ... --out-folder ...")
     command = argv[0].replace("-", "_")
-    spec = {name: (typ, default) for name, typ, default in _SIGNATURE}
+    spec = {name: (typ, default) for name, typ, default in _SIGNATURES.get(command, _SIGNATURE)}
     kwargs = {name: default for name, (typ, default) in spec.items()}
     i = 1
     while i < len(argv):
@@ -169,12 +179,93 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
                             return_ctrl_norm_score=flag_return_ctrl_norm_score, min_genes=10, on_result=write)
 
 
+def perform_downstream(h5ad_file, score_file, out_folder, group_analysis=None, corr_analysis=None,
+                       gene_analysis=None, flag_filter_data=True, flag_raw_count=True, min_genes=250, min_cells=50,
+                       knn_n_neighbors=15, knn_n_pcs=20):
+    """Group / cell-variable / gene analyses of precomputed ``.full_score.gz`` files (bin/scdrs:558-816):
+    ``<trait>.scdrs_group.<annot>``, ``<trait>.scdrs_cell_corr``, ``<trait>.scdrs_gene`` in ``out_folder``.
+
+    The group analysis needs the cells' neighbour graph.  The reference builds it with scanpy
+    (``sc.pp.pca`` + ``sc.pp.neighbors``, bin/scdrs:748-760) when the file has none; scanpy is not part of this
+    build, so the ``.h5ad`` must carry ``obsp["connectivities"]`` (any file that went through
+    ``sc.pp.neighbors``)."""
+    sys_start_time = time.time()
+    header = get_cli_head()
+    header += "Call: scdrs perform-downstream \\\n"
+    assert sum([group_analysis is not None, corr_analysis is not None, gene_analysis is not None]) > 0, \
+        "Expect at least one of `--group_analysis`, `--corr_analysis`, `--gene_analyis`"
+    if group_analysis is not None:
+        group_analysis = group_analysis.split(",") if isinstance(group_analysis, str) else list(group_analysis)
+    if corr_analysis is not None:
+        corr_analysis = corr_analysis.split(",") if isinstance(corr_analysis, str) else list(corr_analysis)
+    for key, val in [("h5ad-file", h5ad_file), ("score-file", score_file), ("out-folder", out_folder),
+                     ("group-analysis", None if group_analysis is None else ",".join(group_analysis)),
+                     ("corr-analysis", None if corr_analysis is None else ",".join(corr_analysis)),
+                     ("gene-analysis", gene_analysis), ("flag-filter-data", flag_filter_data),
+                     ("flag-raw-count", flag_raw_count), ("min-genes", min_genes), ("min-cells", min_cells),
+                     ("knn-n-neighbors", knn_n_neighbors)]:
+        if val is not None:
+            header += "--%s %s \\\n" % (key, val)
+    header += "--knn-n-pcs %s\n" % knn_n_pcs
+    print(header)
+
+    adata = util.load_h5ad(h5ad_file=h5ad_file, flag_filter_data=flag_filter_data, flag_raw_count=flag_raw_count,
+                           min_genes=min_genes, min_cells=min_cells)
+    print("--h5ad-file loaded: n_cell=%d, n_gene=%d (sys_time=%0.1fs)"
+          % (adata.shape[0], adata.shape[1], time.time() - sys_start_time))
+    dict_score = util.load_scdrs_score(score_file)
+    print("--score-file loaded: n_trait=%d (sys_time=%0.1fs)" % (len(dict_score), time.time() - sys_start_time))
+    assert len(dict_score) > 0, "Expect at least 1 score file."
+    if group_analysis is not None:
+        assert len(set(group_analysis) - set(adata.obs)) == 0, \
+            "Missing --group-analysis variables from `adata.obs.columns`."
+        if "connectivities" not in adata.obsp:
+            raise ValueError("`connectivities` not found in the .h5ad's obsp; run `sc.pp.neighbors(adata, n_neighbors=%d, "
+                             "n_pcs=%d)` and save the file first (scanpy's graph construction is not part of scdrs_b200)"
+                             % (knn_n_neighbors, knn_n_pcs))
+    if corr_analysis is not None:
+        assert len(set(corr_analysis) - set(adata.obs)) == 0, \
+            "Missing --corr-analysis variables from `adata.obs.columns`."
+    os.makedirs(out_folder, exist_ok=True)
+    method = scdrs_b200.method
+
+    if group_analysis is not None:
+        print("Performing scDRS group-analysis")
+        for trait in dict_score:
+            dict_df_res = method.downstream_group_analysis(adata=adata, df_full_score=dict_score[trait],
+                                                           group_cols=group_analysis)
+            for group_col in group_analysis:
+                name = "%s.scdrs_group.%s" % (trait, group_col.replace(" ", "_").replace(",", "_"))
+                dict_df_res[group_col].to_csv(os.path.join(out_folder, name), sep="\t", index=True)
+            print("Finish group-analysis for %s (sys_time=%0.1fs)" % (trait, time.time() - sys_start_time))
+        print("")
+    if corr_analysis is not None:
+        print("Performing scDRS corr-analysis")
+        for trait in dict_score:
+            df_res = method.downstream_corr_analysis(adata=adata, df_full_score=dict_score[trait], var_cols=corr_analysis)
+            df_res.to_csv(os.path.join(out_folder, "%s.scdrs_cell_corr" % trait), sep="\t", index=True)
+            print("Finish corr-analysis for %s (sys_time=%0.1fs)" % (trait, time.time() - sys_start_time))
+        print("")
+    if gene_analysis is not None:
+        print("Performing scDRS gene-analysis")
+        for trait in dict_score:
+            df_res = method.downstream_gene_analysis(adata=adata, df_full_score=dict_score[trait])
+            df_res.to_csv(os.path.join(out_folder, "%s.scdrs_gene" % trait), sep="\t", index=True)
+            print("Finish gene-analysis for %s (sys_time=%0.1fs)" % (trait, time.time() - sys_start_time))
+        print("")
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     command, kwargs = parse_cli(argv)
+    if command == "perform_downstream":
+        missing = [k for k in ("h5ad_file", "score_file", "out_folder") if kwargs[k] is None]
+        if missing:
+            raise SystemExit("missing required option(s): " + ", ".join("--" + m.replace("_", "-") for m in missing))
+        return perform_downstream(**kwargs)
     if command != "compute_score":
-        raise SystemExit("scdrs_b200 implements `compute-score` only (got %r); munge-gs and "
-                         "perform-downstream are outside the accelerated path" % argv[0])
+        raise SystemExit("scdrs_b200 implements `compute-score` and `perform-downstream` (got %r); munge-gs is "
+                         "outside the accelerated path" % argv[0])
     missing = [k for k in ("h5ad_file", "h5ad_species", "gs_file", "gs_species", "out_folder") if kwargs[k] is None]
     if missing:
         raise SystemExit("missing required option(s): " + ", ".join("--" + m.replace("_", "-") for m in missing))

@@ -617,19 +617,25 @@ int scdrs_gene_mean_xtc(scdrs_ctx* c, int32_t k, const double* cov_mat, float* g
 }
 
 // ---- downstream analyses of one trait's score matrix (downstream.cu) ------------------------------
-int scdrs_ds_set_scores(scdrs_ctx* c, int64_t n_cell, int32_t ncol, const void* mat, int32_t is_f32) {
+int scdrs_ds_set_scores(scdrs_ctx* c, int64_t n_cell, int32_t ncol, const void* frame, int32_t is_f32,
+                        int64_t n_elem, int64_t row_stride, int64_t col_stride, const int32_t* cols) {
     CTX_GUARD(c);
-    SCDRS_CHECK(mat != nullptr && n_cell > 0 && ncol > 0, "empty score matrix");
-    const size_t m = (size_t)n_cell * ncol;
-    c->ds_n = 0;
-    SCDRS_TRY(c->ds_S.reserve(m * sizeof(double)));
-    if (is_f32) {
-        SCDRS_TRY(h2d_big(c, c->ds_M, mat, m * sizeof(float)));
-        SCDRS_TRY(ds_widen(c, (int64_t)m, c->ds_M.as<float>(), c->ds_S.as<double>()));
-    } else {
-        SCDRS_TRY(h2d_big(c, c->ds_S, mat, m * sizeof(double)));
+    SCDRS_CHECK(frame != nullptr && cols != nullptr && n_cell > 0 && ncol > 0, "empty score matrix");
+    SCDRS_CHECK(row_stride == 1 || col_stride == 1,
+                "the frame must be row-major (col_stride 1) or column-major (row_stride 1)");
+    for (int j = 0; j < ncol; ++j) {
+        const int64_t last = (n_cell - 1) * row_stride + (int64_t)cols[j] * col_stride;
+        SCDRS_CHECK(cols[j] >= 0 && last < n_elem, "score column %d outside the frame", j);
     }
-    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    c->ds_n = 0;
+    DevBuf d_cols;
+    SCDRS_TRY(c->ds_S.reserve((size_t)n_cell * ncol * sizeof(double)));
+    SCDRS_TRY(h2d_big(c, c->ds_M, frame, (size_t)n_elem * (is_f32 ? sizeof(float) : sizeof(double))));
+    int rc = h2d(c, d_cols, cols, (size_t)ncol * sizeof(int32_t));
+    if (rc == 0) rc = ds_import(c, n_cell, ncol, is_f32, row_stride, col_stride, d_cols.as<int32_t>(), c->ds_M.p, c->ds_S.as<double>());
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    d_cols.release();
+    if (rc) return rc;
     c->ds_n = n_cell;
     c->ds_ncol = ncol;
     c->ds_f32 = is_f32 != 0;

@@ -178,7 +178,8 @@ int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells,
                       float* h_n_counts);
 
 // ---- downstream.cu ----------------------------------------------------------------------------
-int ds_widen(scdrs_ctx* c, int64_t m, const float* dev_in, double* dev_out);
+int ds_import(scdrs_ctx* c, int64_t n, int ncol, int is_f32, int64_t rs, int64_t cs, const int32_t* dev_cols,
+              const void* dev_src, double* dev_S);
 int ds_corr(scdrs_ctx* c, int n_var, const double* dev_vars, double* dev_corr);
 int ds_group_stats(scdrs_ctx* c, int n_group, const int64_t* h_gptr, const int64_t* d_order, const int64_t* d_gptr,
                    const int32_t* d_qlo, const double* d_qgamma, double* d_quant, int geary_mode,

@@ -442,13 +442,47 @@ int ds_group_stats(scdrs_ctx* c, int n_group, const int64_t* h_gptr, const int64
     return 0;
 }
 
-__global__ void ds_f32_to_f64_kernel(int64_t m, const float* __restrict__ in, double* __restrict__ out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (double)in[i];
+// The caller's frame -> S[n x ncol] fp64 row-major: element (r, j) of the scores is src[r * rs + cols[j] * cs]
+// (a row-major frame has cs = 1, a column-major one -- what pandas holds after most operations -- rs = 1).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ds_import_rowmajor_kernel(int64_t n, int ncol, int64_t rs, const int32_t* __restrict__ cols, const T* __restrict__ src,
+                          double* __restrict__ S) {
+    const int64_t r = blockIdx.x;
+    for (int j = threadIdx.x; j < ncol; j += blockDim.x) S[r * ncol + j] = (double)src[r * rs + cols[j]];
 }
 
-int ds_widen(scdrs_ctx* c, int64_t m, const float* dev_in, double* dev_out) {
-    ds_f32_to_f64_kernel<<<kNumSM * 8, 256, 0, c->stream>>>(m, dev_in, dev_out);
+template <typename T>
+__global__ void __launch_bounds__(256)
+ds_import_colmajor_kernel(int64_t n, int ncol, int64_t cs, const int32_t* __restrict__ cols, const T* __restrict__ src,
+                          double* __restrict__ S) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    for (int k = ty; k < 32; k += 8) {
+        const int j = j0 + k;
+        const int64_t r = r0 + tx;
+        tile[k][tx] = (j < ncol && r < n) ? (double)src[(int64_t)cols[j] * cs + r] : 0.0;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k;
+        const int j = j0 + tx;
+        if (r < n && j < ncol) S[r * ncol + j] = tile[tx][k];
+    }
+}
+
+int ds_import(scdrs_ctx* c, int64_t n, int ncol, int is_f32, int64_t rs, int64_t cs, const int32_t* dev_cols,
+              const void* dev_src, double* dev_S) {
+    if (cs == 1) {
+        if (is_f32) ds_import_rowmajor_kernel<float><<<(unsigned)n, 256, 0, c->stream>>>(n, ncol, rs, dev_cols, (const float*)dev_src, dev_S);
+        else ds_import_rowmajor_kernel<double><<<(unsigned)n, 256, 0, c->stream>>>(n, ncol, rs, dev_cols, (const double*)dev_src, dev_S);
+    } else {
+        const dim3 g((unsigned)((n + 31) / 32), (ncol + 31) / 32);
+        if (is_f32) ds_import_colmajor_kernel<float><<<g, 256, 0, c->stream>>>(n, ncol, cs, dev_cols, (const float*)dev_src, dev_S);
+        else ds_import_colmajor_kernel<double><<<g, 256, 0, c->stream>>>(n, ncol, cs, dev_cols, (const double*)dev_src, dev_S);
+    }
     SCDRS_LAUNCH_CHECK(c);
     return 0;
 }

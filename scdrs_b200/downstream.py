@@ -25,19 +25,37 @@ def _ctx():
     return _scratch_context()
 
 
-def _take_rows(df, rows, cols):
-    """df.loc[rows, cols] as one C-contiguous array (float32 when every column is, else float64)."""
+def _align(adata, df_full_score):
+    """``cell_list = sorted(set(adata.obs_names) & set(df_full_score.index))`` (scdrs/method.py:757) as row
+    numbers: (rows of df_full_score, rows of adata), both in cell_list order."""
+    in_adata = adata.obs_names.get_indexer(df_full_score.index)
+    if df_full_score.index.is_unique and adata.obs_names.is_unique:
+        df_rows = np.nonzero(in_adata >= 0)[0]
+        names = np.asarray(df_full_score.index.values[df_rows], dtype=object)
+        by_name = np.argsort(names, kind="stable")
+        return df_rows[by_name], in_adata[df_rows][by_name]
+    cell_list = sorted(set(adata.obs_names) & set(df_full_score.index))
+    return df_full_score.index.get_indexer(cell_list), adata.obs_names.get_indexer(cell_list)
+
+
+def _upload_scores(ctx, df, cols, rows=None):
+    """Put df[cols] on the device.  When every row takes part the frame's memory is uploaded as it is (no
+    host copy, the device picks the columns) and the rows keep the frame's order; otherwise the selected
+    rows are gathered first.  Returns the device row of every selected cell."""
+    n = df.shape[0]
+    whole = rows is None or (len(rows) == n)
+    same = len(set(df.dtypes)) == 1 and df.dtypes.iloc[0] in (np.float32, np.float64)
+    if whole and same:
+        ctx.ds_set_scores(df.to_numpy(copy=False), df.columns.get_indexer(cols))
+        return np.arange(n, dtype=np.int64) if rows is None else np.asarray(rows, dtype=np.int64)
     sub = df[cols]
-    if not sub.index.equals(pd.Index(rows)):
-        sub = sub.loc[rows]
     f32 = all(dt == np.float32 for dt in sub.dtypes)
-    return np.ascontiguousarray(sub.to_numpy(dtype=np.float32 if f32 else np.float64))
-
-
-def _positions(adata, names):
-    idx = adata.obs_names.get_indexer(names)
-    assert (idx >= 0).all(), "cells missing from adata.obs_names"
-    return idx
+    vals = sub.to_numpy(dtype=np.float32 if f32 else np.float64)
+    if whole:
+        ctx.ds_set_scores(vals)
+        return np.arange(n, dtype=np.int64) if rows is None else np.asarray(rows, dtype=np.int64)
+    ctx.ds_set_scores(np.ascontiguousarray(vals[rows]))
+    return np.arange(len(rows), dtype=np.int64)
 
 
 def _quantile_positions(sizes, q):
@@ -127,8 +145,9 @@ def gearys_c(adata, vals):
         return ((N - 1) * total[0, 0]) / (2 * W * denom[0, 0])
 
 
-def _gearys_by_group(ctx, codes, n_group, graph, geary_mode, q=None):
-    """Device pass for one grouping of the uploaded score matrix: (quantile or None, C[n_group x ncol])."""
+def _gearys_by_group(ctx, codes, n_group, graph, geary_mode, q=None, dev_rows=None):
+    """Device pass for one grouping of the uploaded score matrix: (quantile or None, C[n_group x ncol]).
+    codes / graph follow the caller's cell order; dev_rows[i] = row of cell i in the uploaded matrix."""
     order, grp_ptr = _group_layout(codes, n_group)
     sizes = np.diff(grp_ptr)
     q_lo = q_gamma = None
@@ -137,7 +156,8 @@ def _gearys_by_group(ctx, codes, n_group, graph, geary_mode, q=None):
     parts = None
     if geary_mode:
         parts = _group_graph(graph, codes, order)
-    quant, total, denom = ctx.ds_group_stats(order, grp_ptr, q_lo, q_gamma, geary_mode, parts)
+    quant, total, denom = ctx.ds_group_stats(order if dev_rows is None else dev_rows[order], grp_ptr, q_lo, q_gamma,
+                                             geary_mode, parts)
     C = None
     if geary_mode:
         w_sum = _group_weight_sums(parts, grp_ptr)
@@ -153,27 +173,30 @@ def test_gearysc(adata, df_full_score, groupby, opt="control_distribution_match"
     df_meta = adata.obs
     labels = df_meta[groupby]
     index_groups = list(labels.unique())
-    groups = [g for g, _ in df_meta.groupby(groupby, observed=True)]           # sorted, non-empty
+    codes, groups = pd.factorize(np.asarray(labels.values, dtype=object), sort=True)   # groupby order: sorted, non-empty
+    groups = list(groups)
     code_of = {g: i for i, g in enumerate(groups)}
-    codes = np.array([code_of[g] for g in labels.values], dtype=np.int64)
 
-    mat = _take_rows(df_full_score, df_full_score.index.values, ["norm_score"] + ctrl_cols)
+    ctx = _ctx()
     if opt == "control_distribution_match":
         mode = 1
     elif opt == "control":
         mode = 2
     elif opt == "permutation":
-        # the reference permutes the trait scores of a group once per control, groups in sorted order
         mode = 2
-        mat = mat.astype(np.float64)
+    else:
+        raise NotImplementedError
+    if opt == "permutation":
+        # the reference permutes the trait scores of a group once per control, groups in sorted order
+        mat = np.empty((df_full_score.shape[0], 1 + n_null), np.float64)
+        mat[:, 0] = df_full_score["norm_score"].values
         for g in groups:
             rows = np.nonzero(codes == code_of[g])[0]
             for i_null in range(n_null):
                 mat[rows, 1 + i_null] = np.random.permutation(mat[rows, 0])
+        ctx.ds_set_scores(mat)
     else:
-        raise NotImplementedError
-    ctx = _ctx()
-    ctx.ds_set_scores(mat)
+        _upload_scores(ctx, df_full_score, ["norm_score"] + ctrl_cols)
     _, C = _gearys_by_group(ctx, codes, len(groups), adata.obsp["connectivities"], mode)
 
     df_stats = pd.DataFrame(index=index_groups, columns=["trait"] + [f"null_{i}" for i in range(n_null)], data=np.nan)
@@ -206,16 +229,15 @@ def downstream_group_analysis(adata, df_full_score, group_cols, fdr_thresholds=[
     assert "connectivities" in adata.obsp, "Expect `connectivities` in `adata.obsp`; run `sc.pp.neighbors` first"
     assert len(set(group_cols) - set(adata.obs)) == 0, "Missing `group_cols` variables from `adata.obs.columns`."
 
-    cell_list = sorted(set(adata.obs_names) & set(df_full_score.index))
+    df_rows, rows = _align(adata, df_full_score)            # cell_list order
     control_list = [x for x in df_full_score.columns if x.startswith("ctrl_norm_score")]
     n_ctrl = len(control_list)
-    rows = _positions(adata, cell_list)
-    df_reg = adata.obs.iloc[rows][list(group_cols)].copy()
-    pval = df_full_score["pval"].loc[cell_list].values
+    df_reg = adata.obs.iloc[rows][list(group_cols)]
+    pval = df_full_score["pval"].values[df_rows]
     graph = sparse.csr_matrix(adata.obsp["connectivities"])[rows][:, rows]
 
     ctx = _ctx()
-    ctx.ds_set_scores(_take_rows(df_full_score, cell_list, ["norm_score"] + control_list))
+    dev_rows = _upload_scores(ctx, df_full_score, ["norm_score"] + control_list, df_rows)
     v_fdr = fdr_bh(pval)
 
     dict_df_res = {}
@@ -224,33 +246,36 @@ def downstream_group_analysis(adata, df_full_score, group_cols, fdr_thresholds=[
         res_cols = ["n_cell", "n_ctrl", "assoc_mcp", "assoc_mcz", "hetero_mcp", "hetero_mcz"]
         for fdr_threshold in fdr_thresholds:
             res_cols.append(f"n_fdr_{fdr_threshold}")
-        df_res = pd.DataFrame(index=group_list, columns=res_cols, dtype=np.float32)
+        out = np.full((len(group_list), len(res_cols)), np.nan, np.float32)
+
+        codes, present = pd.factorize(np.asarray(df_reg[group_col].values, dtype=object), sort=True)
+        present = list(present)
+        q95, C = _gearys_by_group(ctx, codes, len(present), graph, 1, q=0.95, dev_rows=dev_rows)
+
+        where = np.array([group_list.index(g) for g in present], dtype=np.int64)
+
+        def put(col, values):
+            out[where, res_cols.index(col)] = values
+
+        put("n_cell", np.bincount(codes, minlength=len(present)))
+        put("n_ctrl", n_ctrl)
+        for fdr_threshold in fdr_thresholds:
+            put(f"n_fdr_{fdr_threshold}", np.bincount(codes, weights=(v_fdr < fdr_threshold), minlength=len(present)))
+        # association: the group's 0.95 quantile against the controls'              :797-806
+        score_q95, v_ctrl_score_q95 = q95[:, 0], q95[:, 1:]
+        put("assoc_mcp", ((v_ctrl_score_q95 >= score_q95[:, None]).sum(axis=1) + 1) / (n_ctrl + 1))
+        put("assoc_mcz", (score_q95 - v_ctrl_score_q95.mean(axis=1)) / v_ctrl_score_q95.std(axis=1))
+        # heterogeneity: Geary's C against the distribution-matched controls        :809-814, 1022-1040
+        trait, null = C[:, 0], C[:, 1:]
+        h_p = ((trait[:, None] > null).sum(axis=1) + 1) / (n_ctrl + 1)
+        h_p[np.isnan(trait)] = np.nan
+        with np.errstate(divide="ignore", invalid="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)            # groups without edges: all NaN
+            h_z = -(trait - np.nanmean(null, axis=1)) / np.nanstd(null, axis=1, ddof=1)
+        put("hetero_mcp", h_p)
+        put("hetero_mcz", h_z)
+        df_res = pd.DataFrame(out, index=group_list, columns=res_cols)
         df_res.index.name = "group"
-
-        labels = df_reg[group_col].values
-        present = [g for g in group_list if (labels == g).any()]
-        code_of = {g: i for i, g in enumerate(present)}
-        codes = np.array([code_of[g] for g in labels], dtype=np.int64)
-        q95, C = _gearys_by_group(ctx, codes, len(present), graph, 1, q=0.95)
-
-        for group in present:
-            k = code_of[group]
-            in_group = codes == k
-            df_res.loc[group, ["n_cell", "n_ctrl"]] = [in_group.sum(), n_ctrl]
-            for fdr_threshold in fdr_thresholds:
-                df_res.loc[group, f"n_fdr_{fdr_threshold}"] = (v_fdr[in_group] < fdr_threshold).sum()
-            # association: the group's 0.95 quantile against the controls'          :797-806
-            score_q95, v_ctrl_score_q95 = q95[k, 0], q95[k, 1:]
-            mc_p = ((v_ctrl_score_q95 >= score_q95).sum() + 1) / (v_ctrl_score_q95.shape[0] + 1)
-            mc_z = (score_q95 - v_ctrl_score_q95.mean()) / v_ctrl_score_q95.std()
-            df_res.loc[group, ["assoc_mcp", "assoc_mcz"]] = [mc_p, mc_z]
-            # heterogeneity: Geary's C against the distribution-matched controls    :809-814, 1022-1040
-            trait, null = C[k, 0], C[k, 1:]
-            h_p = ((trait > null).sum() + 1) / (null.shape[0] + 1) if not np.isnan(trait) else np.nan
-            with np.errstate(divide="ignore", invalid="ignore"), warnings.catch_warnings():
-                warnings.simplefilter("ignore", RuntimeWarning)        # groups without edges: all NaN
-                h_z = -(trait - np.nanmean(null)) / np.nanstd(null, ddof=1) if null.shape[0] > 1 else np.nan
-            df_res.loc[group, ["hetero_mcp", "hetero_mcz"]] = [h_p, h_z]
         dict_df_res[group_col] = df_res
     return dict_df_res
 
@@ -262,14 +287,15 @@ def downstream_corr_analysis(adata, df_full_score, var_cols):
     """Monte-Carlo test of the correlation between cell-level variables and the trait score (drop-in for
     scdrs/method.py:822-865)."""
     assert len(set(var_cols) - set(adata.obs)) == 0, "Missing `var_cols` variables from `adata.obs.columns`."
-    cell_list = sorted(set(adata.obs_names) & set(df_full_score.index))
+    df_rows, rows = _align(adata, df_full_score)            # cell_list order
     control_list = [x for x in df_full_score.columns if x.startswith("ctrl_norm_score")]
     n_ctrl = len(control_list)
-    rows = _positions(adata, cell_list)
-    variables = np.stack([np.asarray(adata.obs[v].values[rows], dtype=np.float64) for v in var_cols])
 
     ctx = _ctx()
-    ctx.ds_set_scores(_take_rows(df_full_score, cell_list, ["norm_score"] + control_list))
+    dev_rows = _upload_scores(ctx, df_full_score, ["norm_score"] + control_list, df_rows)
+    variables = np.empty((len(var_cols), len(rows)), np.float64)
+    for i, v in enumerate(var_cols):                        # each variable in the order of the uploaded rows
+        variables[i, dev_rows] = np.asarray(adata.obs[v].values[rows], dtype=np.float64)
     corr = ctx.ds_corr(variables)
 
     df_res = pd.DataFrame(index=var_cols, columns=["n_ctrl", "corr_mcp", "corr_mcz"], dtype=np.float32)
@@ -346,7 +372,7 @@ def downstream_gene_analysis(adata, df_full_score):
         v_y = np.asarray(y.reindex(adata.obs_names).values, dtype=np.float64).reshape(-1, 1)
         v_corr = _corr_on_device(adata, v_y, centered_var=not sparse.issparse(adata.X)).reshape([-1])
     else:
-        v_corr = _pearson_corr(adata[_positions(adata, cell_list)].X, y.values)
+        v_corr = _pearson_corr(adata[adata.obs_names.get_indexer(cell_list)].X, y.values)
     df_res = pd.DataFrame(index=adata.var_names, columns=["CORR", "RANK"], dtype=np.float32)
     df_res["CORR"] = v_corr
     df_res.sort_values("CORR", ascending=False, inplace=True)

@@ -82,9 +82,11 @@ def preprocess_counts(adata, flag_filter_data=False, flag_raw_count=True, min_ge
                 var["n_cells"] = out["n_cells"][keep_g]
             if flag_raw_count:
                 obs["n_counts"] = out["n_counts"][keep_c]
-            adata = AnnData(X, obs, var, adata.uns)
+            rows = np.nonzero(keep_c)[0]
+            adata = AnnData(X, obs, var, adata.uns, {k: v[rows][:, rows] for k, v in getattr(adata, "obsp", {}).items()})
         elif not (isinstance(adata.X, sparse.csr_matrix) and adata.X.dtype == np.float32):
-            adata = AnnData(sparse.csr_matrix((data, indices, indptr), shape=adata.shape), adata.obs, adata.var, adata.uns)
+            adata = AnnData(sparse.csr_matrix((data, indices, indptr), shape=adata.shape), adata.obs, adata.var, adata.uns,
+                            dict(getattr(adata, "obsp", {})))
     except BaseException:
         ctx.close()
         raise
@@ -115,8 +117,33 @@ def _preprocess_counts_dense(adata, flag_filter_data, flag_raw_count, min_genes,
             counts = counts[keep]
         adata.obs["n_counts"] = counts
         scale = (1e4 / counts).astype(np.float32)
-        adata = AnnData(np.log1p(np.asarray(adata.X, dtype=np.float32) * scale[:, None]), adata.obs, adata.var, adata.uns)
+        adata = AnnData(np.log1p(np.asarray(adata.X, dtype=np.float32) * scale[:, None]), adata.obs, adata.var, adata.uns,
+                        adata.obsp)
     return adata
+
+
+def load_scdrs_score(score_file, obs_names=None):
+    """Load ``.full_score.gz`` files keyed by trait; "@" in the file name is a wildcard (drop-in for
+    scdrs/util.py:95-149).  Files sharing fewer than 10% of ``obs_names`` are skipped."""
+    import fnmatch
+
+    assert score_file.endswith("full_score.gz"), "Expect scDRS .full_score.gz files for score_file"
+    score_file_pattern = score_file.split(os.path.sep)[-1]
+    score_dir = score_file.replace(os.path.sep + score_file_pattern, "")
+    score_file_list = [x for x in os.listdir(score_dir) if fnmatch.fnmatch(x, score_file_pattern.replace("@", "*"))]
+    print("Score file folder: %s" % score_dir)
+    print("Find %d score files: %s" % (len(score_file_list), ",".join(score_file_list)))
+    dict_score = {}
+    for name in score_file_list:
+        temp_df = pd.read_csv(score_dir + os.path.sep + name, sep="\t", index_col=0)
+        temp_df.index = [str(x) for x in temp_df.index]
+        if obs_names is not None:
+            n_cell_overlap = len(set(obs_names) & set(temp_df.index))
+            if n_cell_overlap < 0.1 * len(obs_names):
+                print("WARNING: %s skipped, containing %d/%d target cells" % (name, n_cell_overlap, len(obs_names)))
+                continue
+        dict_score[name.replace(".full_score.gz", "")] = temp_df
+    return dict_score
 
 
 def load_homolog_mapping(src_species: str, dst_species: str) -> dict:

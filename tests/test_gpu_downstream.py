@@ -186,3 +186,26 @@ def test_group_analysis_argument_checks(method):
     adata.obsp.pop("connectivities")
     with pytest.raises(AssertionError, match="Expect `connectivities`"):
         method.downstream_group_analysis(adata, df, ["grp"])
+
+
+def test_cli_perform_downstream(native_lib, tmp_path):
+    """tests/test_CLI.py:137-190 of the reference (corr and gene analyses; the toy .h5ad carries no neighbour
+    graph, so the group analysis must ask for one)."""
+    from scdrs_b200 import cli
+
+    args = ["perform-downstream", "--h5ad_file", os.path.join(helpers.TOY, "toydata_mouse.h5ad"),
+            "--score-file", os.path.join(helpers.TOY, "@.full_score.gz"), "--flag-filter-data", "False",
+            "--flag-raw-count", "False", "--knn-n-neighbors", "15", "--knn-n-pcs", "20", "--out-folder", str(tmp_path)]
+    cli.main(args + ["--corr-analysis", "causal_variable,non_causal_variable,covariate"])
+    cli.main(args + ["--gene-analysis"])
+    prefix = "toydata_gs_mouse.ref_Ctrl20_CovConstCovariate"
+    for suffix in ["scdrs_gene", "scdrs_cell_corr"]:
+        df_res = pd.read_csv(os.path.join(str(tmp_path), "%s.%s" % (prefix, suffix)), sep="\t", index_col=0)
+        df_ref = pd.read_csv(os.path.join(helpers.TOY, "%s.%s" % (prefix, suffix)), sep="\t", index_col=0)
+        if suffix == "scdrs_gene":
+            np.testing.assert_allclose(df_res.loc[df_ref.index, "CORR"].values, df_ref["CORR"].values, rtol=1e-5, atol=1e-7)
+        else:
+            assert list(df_res.index) == list(df_ref.index)
+            np.testing.assert_allclose(df_res.values, df_ref.values, rtol=1e-5)
+    with pytest.raises(ValueError, match="connectivities"):
+        cli.main(args + ["--group-analysis", "cell_type"])
