@@ -666,6 +666,38 @@ def test_full_size_config4_two_kernels_agree(native_lib):
     scdrs_b200.clear_device_cache()
 
 
+def test_full_size_config5_shard_two_kernels_agree(native_lib):
+    """One GPU's share of BASELINE config 5 (4M x 30k over 8 GPUs: 500,000 cells x 30,000 genes, 1.5e9 stored
+    entries, n_ctrl = 5000 -> five column tiles of the fixed-point scatter, 2.5e9 pooled null values per shard):
+    same size-independent check as for config 4."""
+    import torch
+
+    import bench
+    import scdrs_b200
+
+    free, _total = torch.cuda.mem_get_info(0)
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs 100 GB of free device memory")
+
+    class Args:
+        n_cell, n_gene, density, n_trait, n_trait_gene = 500000, 30000, 0.10, 1, 1000
+
+    adata, traits, info = bench.build_workload(Args, 0, torch.device("cuda", 0))
+    assert info["nnz"] > 1.4e9
+    genes, w = traits["trait_00"]
+    fx, kind = _score_in_mode("fixed", adata, genes, w, n_ctrl=5000)
+    assert kind[0] == "fixed"
+    f64, kind = _score_in_mode("f64", adata, genes, w, n_ctrl=5000)
+    assert kind[0] == "f64"
+    assert np.isfinite(fx["norm_score"].values).all()
+    assert np.allclose(fx["raw_score"].values, f64["raw_score"].values, rtol=1e-6, atol=0)
+    assert np.abs(fx["norm_score"].values - f64["norm_score"].values).max() < 1e-5
+    assert (fx["mc_pval"].values != f64["mc_pval"].values).mean() < 1e-3
+    rel = np.abs(fx["pval"].values.astype(np.float64) - f64["pval"].values) / f64["pval"].values
+    assert rel.max() < 1e-3
+    scdrs_b200.clear_device_cache()
+
+
 # ---- the step before the path: load_h5ad's checks, filters and normalisation on the device -----------
 def _raw_counts(n_cell, n_gene, seed):
     rng = np.random.default_rng(seed)
