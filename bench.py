@@ -285,11 +285,23 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def baseline_config_name(args, n_gpus):
+    """Which of BASELINE.json's configs the synthetic shape corresponds to."""
+    total = args.n_cell * n_gpus
+    if args.n_gene == 30000 and args.n_ctrl == 5000 and total >= 3500000:
+        return "BASELINE configs[4]"
+    if args.n_gene == 20000 and args.n_ctrl == 1000 and total >= 1000000 and args.n_cell != 110096:
+        return "BASELINE configs[3]"
+    if (args.n_cell, args.n_gene, args.n_ctrl) == (110096, 20000, 1000):
+        return "BASELINE configs[2]" if getattr(args, "weighted", False) else "BASELINE configs[1]"
+    return "custom shape"
+
+
 def workload_config(args, n_gpus):
     return {
-        "workload": "TMS-FACS-shaped synthetic (BASELINE configs[1]): %d cells x %d genes per GPU, %.0f%% nnz, "
+        "workload": "TMS-FACS-shaped synthetic (%s): %d cells x %d genes per GPU, %.0f%% nnz, "
                     "%d %s %d-gene traits, 4 covariates (implicit covariate correction), n_ctrl=%d, "
-                    "weight_opt=vs, ctrl_match_key=mean_var" % (args.n_cell, args.n_gene, 100 * args.density,
+                    "weight_opt=vs, ctrl_match_key=mean_var" % (baseline_config_name(args, n_gpus), args.n_cell, args.n_gene, 100 * args.density,
                                                                args.n_trait, "weighted" if getattr(args, "weighted", False) else "binary",
                                                                args.n_trait_gene, args.n_ctrl),
         "n_cell_per_gpu": args.n_cell, "n_gene": args.n_gene, "n_trait": args.n_trait, "n_ctrl": args.n_ctrl,
