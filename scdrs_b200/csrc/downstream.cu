@@ -242,43 +242,51 @@ ds_gather_rows_kernel(int64_t n, int ncol, const double* __restrict__ S, const i
 }
 
 // per (group, column) of the row-major matrix in group order: sum (x - mean)^2 (two passes; the denominator
-// of Geary's C, scdrs/method.py:1081)
+// of Geary's C, scdrs/method.py:1081).  A group's rows are split over kSsSplit blocks (one group may hold half
+// of all cells); partial results are combined in split order.
+constexpr int kSsSplit = 16;
+
+// pass = 0: part[g][z][col] = sum of the split's rows; pass = 1: sum (x - mean)^2 with mean from pass 0
 __global__ void __launch_bounds__(256)
-ds_group_ss_kernel(int ncol, const int64_t* __restrict__ gptr, const double* __restrict__ M, double* __restrict__ out) {
+ds_group_ss_kernel(int ncol, int pass, const int64_t* __restrict__ gptr, const double* __restrict__ M,
+                   const double* __restrict__ sums, double* __restrict__ part) {
     __shared__ double sh[8][33];
-    __shared__ double mean[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int g = blockIdx.y;
+    const int g = blockIdx.y, z = blockIdx.z;
     const int col = blockIdx.x * 32 + tx;
     const int64_t a = gptr[g], b = gptr[g + 1];
-    double s = 0.0;
-    if (col < ncol)
-        for (int64_t p = a + ty; p < b; p += 8) s += M[p * ncol + col];
-    sh[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0) {
+    const int64_t r0 = a + (b - a) * z / kSsSplit, r1 = a + (b - a) * (z + 1) / kSsSplit;
+    double m = 0.0;
+    if (pass == 1 && col < ncol) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sh[k][tx];
-        mean[tx] = t / (double)(b - a);
+        for (int k = 0; k < kSsSplit; ++k) t += sums[((size_t)g * kSsSplit + k) * ncol + col];
+        m = t / (double)(b - a);
     }
-    __syncthreads();
-    const double m = mean[tx];
-    s = 0.0;
+    double s = 0.0;
     if (col < ncol)
-        for (int64_t p = a + ty; p < b; p += 8) {
+        for (int64_t p = r0 + ty; p < r1; p += 8) {
             const double d = M[p * ncol + col] - m;
-            s += d * d;
+            s += pass == 1 ? d * d : d;
         }
-    __syncthreads();
     sh[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && col < ncol) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += sh[k][tx];
-        out[(size_t)g * ncol + col] = t;
+        part[((size_t)g * kSsSplit + z) * ncol + col] = t;
     }
+}
+
+__global__ void ds_group_ss_finish_kernel(int ncol, const double* __restrict__ part, double* __restrict__ out) {
+    const int g = blockIdx.y;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSsSplit; ++k) t += part[((size_t)g * kSsSplit + k) * ncol + col];
+    out[(size_t)g * ncol + col] = t;
 }
 
 // Geary's C numerators: sum over the stored within-group edges (p, q) of w (x_p - x_q)^2, for every column at
@@ -324,15 +332,26 @@ ds_geary_kernel(int ncol, const int64_t* __restrict__ chunk_p0, const int32_t* _
     }
 }
 
-// totals per group: partial sums added in chunk order (fixed, so results repeat bit for bit)
-__global__ void ds_geary_reduce_kernel(int ncol, const int64_t* __restrict__ grp_chunk_ptr, const double* __restrict__ part,
-                                       double* __restrict__ out) {
+// totals per group: eight interleaved running sums over the group's chunks, combined in a fixed order
+// (results repeat bit for bit)
+__global__ void __launch_bounds__(256)
+ds_geary_reduce_kernel(int ncol, const int64_t* __restrict__ grp_chunk_ptr, const double* __restrict__ part,
+                       double* __restrict__ out) {
+    __shared__ double sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncol) return;
+    const int col = blockIdx.x * 32 + tx;
     double t = 0.0;
-    for (int64_t k = grp_chunk_ptr[g]; k < grp_chunk_ptr[g + 1]; ++k) t += part[(size_t)k * ncol + col];
-    out[(size_t)g * ncol + col] = t;
+    if (col < ncol)
+        for (int64_t k = grp_chunk_ptr[g] + ty; k < grp_chunk_ptr[g + 1]; k += 8) t += part[(size_t)k * ncol + col];
+    sh[ty][tx] = t;
+    __syncthreads();
+    if (ty == 0 && col < ncol) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += sh[k][tx];
+        out[(size_t)g * ncol + col] = r;
+    }
 }
 
 // Everything per grouping.  dev pointers: order[n], gptr[n_group + 1] (int64), q_lo / q_gamma per group (or null),
@@ -407,8 +426,15 @@ int ds_group_stats(scdrs_ctx* c, int n_group, const int64_t* h_gptr, const int64
         SCDRS_LAUNCH_CHECK(c);
     }
     if (geary_mode != 0) {
-        const dim3 gs((ncol + 31) / 32, n_group);
-        ds_group_ss_kernel<<<gs, 256, 0, c->stream>>>(ncol, d_gptr, M, d_denom);
+        const dim3 gs((ncol + 31) / 32, n_group, kSsSplit);
+        SCDRS_TRY(c->ds_tmp.reserve((size_t)2 * n_group * kSsSplit * ncol * sizeof(double)));
+        double* ss_sum = c->ds_tmp.as<double>();
+        double* ss_part = ss_sum + (size_t)n_group * kSsSplit * ncol;
+        ds_group_ss_kernel<<<gs, 256, 0, c->stream>>>(ncol, 0, d_gptr, M, nullptr, ss_sum);
+        SCDRS_LAUNCH_CHECK(c);
+        ds_group_ss_kernel<<<gs, 256, 0, c->stream>>>(ncol, 1, d_gptr, M, ss_sum, ss_part);
+        SCDRS_LAUNCH_CHECK(c);
+        ds_group_ss_finish_kernel<<<dim3((ncol + 255) / 256, n_group), 256, 0, c->stream>>>(ncol, ss_part, d_denom);
         SCDRS_LAUNCH_CHECK(c);
         // chunks of up to kGearyRows cells that never straddle a group
         std::vector<int64_t> cp0, gcp(n_group + 1, 0);
@@ -434,7 +460,7 @@ int ds_group_stats(scdrs_ctx* c, int n_group, const int64_t* h_gptr, const int64
                                                                  c->ds_part.as<double>());
             SCDRS_LAUNCH_CHECK(c);
         }
-        const dim3 gr((ncol + 255) / 256, n_group);
+        const dim3 gr((ncol + 31) / 32, n_group);
         ds_geary_reduce_kernel<<<gr, 256, 0, c->stream>>>(ncol, d_gcp, c->ds_part.as<double>(), d_total);
         SCDRS_LAUNCH_CHECK(c);
         SCDRS_CUDA(cudaStreamSynchronize(c->stream));     // the chunk vectors go out of scope
