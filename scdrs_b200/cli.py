@@ -30,7 +30,11 @@ _SIGNATURE_DOWNSTREAM = [
     ("flag_raw_count", bool, True), ("min_genes", int, 250), ("min_cells", int, 50), ("knn_n_neighbors", int, 15),
     ("knn_n_pcs", int, 20),
 ]
-_SIGNATURES = {"compute_score": _SIGNATURE, "perform_downstream": _SIGNATURE_DOWNSTREAM}
+_SIGNATURE_MUNGE = [
+    ("out_file", str, None), ("pval_file", str, None), ("zscore_file", str, None), ("weight", str, "zscore"),
+    ("fdr", float, None), ("fwer", float, None), ("n_min", int, 100), ("n_max", int, 1000),
+]
+_SIGNATURES = {"compute_score": _SIGNATURE, "perform_downstream": _SIGNATURE_DOWNSTREAM, "munge_gs": _SIGNATURE_MUNGE}
 
 
 def get_cli_head():
@@ -255,6 +259,67 @@ def perform_downstream(h5ad_file, score_file, out_folder, group_analysis=None, c
         print("")
 
 
+def _read_gene_table(path, what):
+    """A GENE x trait table of floats; rows without a gene name dropped, duplicate names refused."""
+    df = pd.read_csv(path, sep="\t", index_col=0)
+    assert df.index.name == "GENE", "Header of the first column should be `GENE`."
+    for col in df.columns:
+        if df[col].dtype != float:
+            raise ValueError(f"Column {col} contains non-float entries. Please check the input file.")
+    print("--%s loaded: n_gene=%d, n_trait=%d" % (what, df.shape[0], df.shape[1]))
+    if df.index.isnull().any():
+        print("Removing %d rows with GENE=NaN" % df.index.isnull().sum())
+        df = df.loc[~df.index.isnull()]
+    if not df.index.is_unique:
+        raise ValueError("Gene names in the provided %s are not unique: " % what,
+                         ",".join(df.index[df.index.duplicated()]),
+                         ". Please make sure the gene names are unique beforehand.")
+    return df
+
+
+def munge_gs(out_file, pval_file=None, zscore_file=None, weight="zscore", fdr=None, fwer=None, n_min=100, n_max=1000):
+    """Gene-level p-values (or one-sided z-scores) per trait -> an scDRS ``.gs`` file (bin/scdrs:307-555): per
+    trait the genes with the smallest p-values -- as many as pass the FDR (Benjamini-Hochberg) or FWER
+    (Bonferroni) threshold, kept between ``n_min`` and ``n_max``, or the top ``n_max`` without a threshold --
+    weighted by their z-score capped at 10 (``weight="zscore"``) or by 1 (``"uniform"``)."""
+    import numpy as np
+
+    assert (pval_file is not None) + (zscore_file is not None) == 1, "One of --pval-file and --zscore-file is expected."
+    assert weight in ["zscore", "uniform"], "--weight needs to be one of 'zscore', 'uniform'"
+    assert (fdr is None) or (fwer is None), "At most one of --fdr and --fwer is allowed."
+    assert out_file is not None, "--out-file is expected."
+    n_min = min(n_min, n_max)
+    print(get_cli_head() + "Call: scdrs munge-gs --weight %s --n-min %s --n-max %s --out-file %s\n"
+          % (weight, n_min, n_max, out_file))
+    if pval_file is not None:
+        df_pval = _read_gene_table(pval_file, "pval-file")
+        if not (df_pval.min(skipna=True).min() > 0 and df_pval.max(skipna=True).max() < 1):
+            print("Warning: pval-file are not all between 0 and 1.")
+    else:
+        df_zscore = _read_gene_table(zscore_file, "zscore-file")
+        if not (df_zscore.min(skipna=True).min() < 0 and df_zscore.max(skipna=True).max() > 1):
+            print("Warning: zscore-file values are all between 0 and 1.")
+        df_pval = df_zscore.apply(lambda col: util.zsc2pval(col.values))
+
+    rows = []
+    for trait in sorted(df_pval.columns):
+        p = df_pval[trait].dropna()
+        if fdr is not None:
+            n_gene = int((util.fdr_bh(p.values) <= fdr).sum())         # BH rejections at level fdr
+        elif fwer is not None:
+            n_gene = int((p.values <= fwer / max(len(p), 1)).sum())    # Bonferroni rejections at level fwer
+        else:
+            n_gene = n_max
+        n_gene = max(min(n_gene, n_max), n_min)
+        p = p.sort_values(ascending=True).iloc[:n_gene]
+        pv = p.values.clip(min=1e-100)
+        w = util.pval2zsc(pv).clip(max=10) if weight == "zscore" else np.ones(len(p))
+        rows.append((trait, ",".join(f"{g}:{x:.5g}" for g, x in zip(p.index, w))))
+    df_gs = pd.DataFrame(rows, columns=["TRAIT", "GENESET"])
+    df_gs.to_csv(out_file, sep="\t", index=False)
+    print("Finish munging %d gene sets" % df_gs.shape[0])
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     command, kwargs = parse_cli(argv)
@@ -263,9 +328,10 @@ def main(argv=None):
         if missing:
             raise SystemExit("missing required option(s): " + ", ".join("--" + m.replace("_", "-") for m in missing))
         return perform_downstream(**kwargs)
+    if command == "munge_gs":
+        return munge_gs(**kwargs)
     if command != "compute_score":
-        raise SystemExit("scdrs_b200 implements `compute-score` and `perform-downstream` (got %r); munge-gs is "
-                         "outside the accelerated path" % argv[0])
+        raise SystemExit("scdrs_b200 implements `compute-score`, `perform-downstream` and `munge-gs` (got %r)" % argv[0])
     missing = [k for k in ("h5ad_file", "h5ad_species", "gs_file", "gs_species", "out_folder") if kwargs[k] is None]
     if missing:
         raise SystemExit("missing required option(s): " + ", ".join("--" + m.replace("_", "-") for m in missing))

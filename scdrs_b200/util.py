@@ -215,6 +215,20 @@ def write_score_file(path, df, n_thread=None):
         df.to_csv(path, sep="\t", index=True, compression="gzip")
 
 
+def zsc2pval(zsc):
+    """One-sided p-value of a z-score (scdrs/util.py:430-435)."""
+    from scipy.stats import norm
+
+    return norm.cdf(-np.asarray(zsc, dtype=np.float64))
+
+
+def pval2zsc(pval):
+    """z-score of a one-sided p-value (scdrs/util.py:438-442)."""
+    from scipy.stats import norm
+
+    return -norm.ppf(np.asarray(pval, dtype=np.float64))
+
+
 def fdr_bh(pvals):
     """Benjamini-Hochberg adjusted p-values (what ``multipletests(method='fdr_bh')[1]`` returns;
     used only for the per-trait log line of the CLI, bin/scdrs:289-303)."""

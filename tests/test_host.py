@@ -250,3 +250,28 @@ def test_score_file_writer_matches_pandas_bytes(native_lib, tmp_path):
     assert gzip.open(str(tmp_path / "e.gz"), "rb").read().decode() == want.getvalue()
     for v in [4.741197, 6.3260064, 0.04761905, 0.0016638935, 1e-5, 123456789.0]:
         assert _native.format_f32(v) == str(np.float32(v))
+
+
+def test_munge_gs_cli_known_answers(tmp_path):
+    """tests/test_CLI.py:74-134 of the reference: p-value and z-score inputs, three selection rules."""
+    from scdrs_b200 import cli
+
+    pd.DataFrame({"GENE": ["OR4F5", "DAZ1", "BPY2B"], "HEIGHT": [0.02, np.nan, 0.4], "BMI": [0.8, 0.02, np.nan]}).to_csv(
+        tmp_path / "pval_file.tsv", sep="\t", index=False)
+    pd.DataFrame({"GENE": ["OR4F5", "DAZ1", "BPY2B"], "HEIGHT": [2.0537, np.nan, 0.25335],
+                  "BMI": [-0.84162, 2.0537, np.nan]}).to_csv(tmp_path / "zscore_file.tsv", sep="\t", index=False)
+    for input_file in ["pval_file", "zscore_file"]:
+        for selection in [["--n-max", "1"], ["--n-min", "1", "--n-max", "3", "--fdr", "0.05"],
+                          ["--n-min", "1", "--n-max", "3", "--fwer", "0.05"]]:
+            out = str(tmp_path / "outfile.gs")
+            cli.main(["munge-gs", "--%s" % input_file, str(tmp_path / (input_file + ".tsv")), "--out-file", out,
+                      "--weight", "zscore"] + selection)
+            df = pd.read_csv(out, sep="\t", index_col=0)
+            assert list(df.index) == ["BMI", "HEIGHT"]
+            assert df.loc["BMI", "GENESET"] == "DAZ1:2.0537"
+            assert df.loc["HEIGHT", "GENESET"] == "OR4F5:2.0537"
+    cli.main(["munge-gs", "--pval-file", str(tmp_path / "pval_file.tsv"), "--out-file", out, "--weight", "uniform", "--n-max", "2"])
+    df = pd.read_csv(out, sep="\t", index_col=0)
+    assert df.loc["HEIGHT", "GENESET"] == "OR4F5:1,BPY2B:1"
+    with pytest.raises(AssertionError, match="One of --pval-file"):
+        cli.main(["munge-gs", "--out-file", out])
