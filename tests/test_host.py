@@ -195,7 +195,7 @@ def test_cli_flag_parsing():
     with pytest.raises(SystemExit):
         cli.parse_cli(["compute-score", "--bogus", "1"])
     with pytest.raises(SystemExit):
-        cli.main(["munge-gs", "--out-file", "x"])
+        cli.main(["plot-something", "--out-file", "x"])
     with pytest.raises(ValueError):
         cli.compute_score("a", "mouse", "g", "mouse", "o", ctrl_match_opt="bad")
 
