@@ -125,6 +125,19 @@ int scdrs_score_trait(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_t n_s_c
                       double* raw_score, float* norm_score, int32_t* mc_count, int64_t* ge_count,
                       float* ctrl_raw, float* ctrl_norm);
 
+/* The same in two halves, for callers that score many traits (`scdrs compute-score` loops over a .gs
+ * file, bin/scdrs:255-274): submit copies the gene sets into pinned memory, enqueues phases 1-5 and the
+ * download of the results into pinned memory, and returns at once with a slot number (two slots: at most
+ * two traits in flight); collect waits for that slot and copies the results out (NULL = skip; the control
+ * matrices only if requested at submit).  The next trait's work is thus queued while the current one runs. */
+int scdrs_score_trait_submit(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                             const int32_t* trait_genes, const double* trait_gw,
+                             const int32_t* ctrl_genes, const double* ctrl_gw, int32_t weight_opt,
+                             int32_t use_var_ratio, int32_t want_ctrl_raw, int32_t want_ctrl_norm,
+                             int32_t* slot_out);
+int scdrs_score_trait_collect(scdrs_ctx* ctx, int32_t slot, double* raw_score, float* norm_score,
+                              int32_t* mc_count, int64_t* ge_count, float* ctrl_raw, float* ctrl_norm);
+
 /* ---- the reference's helper functions as stand-alone calls (host buffers) ------------------ */
 /* _compute_raw_score (scdrs/method.py:377-400) for n_set explicit gene sets with FINAL weights
  * w[n_set x n_s] (already normalised); raw_out[n_cell x n_set] f64. */

@@ -50,6 +50,11 @@ SIGNATURES = {
     "scdrs_score_trait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_score_trait_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_int32)]),
+    "scdrs_score_trait_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "scdrs_compute_raw_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_correct_background": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -231,6 +236,37 @@ class Context:
             WEIGHT_OPT[weight_opt], int(bool(use_var_ratio)), ptr(out["raw_score"]),
             ptr(out["norm_score"]), ptr(out["mc_count"]), ptr(out["ge_count"]), ptr(out["ctrl_raw"]),
             ptr(out["ctrl_norm"])))
+        return out
+
+    def score_trait_submit(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_var_ratio,
+                           want_ctrl_raw=False, want_ctrl_norm=False):
+        """Enqueue one trait without waiting for it; returns a ticket for ``score_trait_collect``.  At most two
+        tickets may be outstanding."""
+        trait_genes = as_c(trait_genes, np.int32)
+        ctrl_genes = as_c(ctrl_genes, np.int32)
+        trait_gw, ctrl_gw = as_c(trait_gw, np.float64), as_c(ctrl_gw, np.float64)
+        n_s = trait_genes.shape[0]
+        n_ctrl, n_sc = ctrl_genes.shape
+        assert ctrl_gw.shape[0] == n_sc and trait_gw.shape[0] == n_s
+        slot = C.c_int32(-1)
+        check(self._L.scdrs_score_trait_submit(
+            self._h, n_ctrl, n_s, n_sc, ptr(trait_genes), ptr(trait_gw), ptr(ctrl_genes), ptr(ctrl_gw),
+            WEIGHT_OPT[weight_opt], int(bool(use_var_ratio)), int(bool(want_ctrl_raw)), int(bool(want_ctrl_norm)),
+            C.byref(slot)))
+        return (slot.value, n_ctrl, bool(want_ctrl_raw), bool(want_ctrl_norm))
+
+    def score_trait_collect(self, ticket):
+        slot, n_ctrl, want_ctrl_raw, want_ctrl_norm = ticket
+        n = self.n_cell
+        out = dict(
+            raw_score=np.empty(n, np.float64), norm_score=np.empty(n, np.float32),
+            mc_count=np.empty(n, np.int32), ge_count=np.empty(n, np.int64),
+            ctrl_raw=np.empty((n, n_ctrl), np.float32) if want_ctrl_raw else None,
+            ctrl_norm=np.empty((n, n_ctrl), np.float32) if want_ctrl_norm else None,
+        )
+        check(self._L.scdrs_score_trait_collect(
+            self._h, slot, ptr(out["raw_score"]), ptr(out["norm_score"]), ptr(out["mc_count"]), ptr(out["ge_count"]),
+            ptr(out["ctrl_raw"]), ptr(out["ctrl_norm"])))
         return out
 
     # -- phases (device pointers are plain ints) --

@@ -214,6 +214,11 @@ int scdrs_ctx_destroy(scdrs_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     release_all(c);
+    for (auto& sl : c->slot) {
+        if (sl.pin_in) cudaFreeHost(sl.pin_in);
+        if (sl.pin_out) cudaFreeHost(sl.pin_out);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     for (int i = 0; i < 4; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -466,7 +471,7 @@ int scdrs_trait_finish(scdrs_ctx* c, const unsigned long long* dev_hist_all, int
         SCDRS_CHECK(c->norm_mat.p != nullptr, "normalised control scores were not kept");
         SCDRS_TRY(d2h(c, ctrl_norm, c->norm_mat.p, (size_t)n * c->n_ctrl * sizeof(float)));
     }
-    SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->finish_async) SCDRS_CUDA(cudaStreamSynchronize(c->stream));     // async: the caller waits on an event
     return 0;
 }
 
@@ -495,6 +500,97 @@ int scdrs_score_trait(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctr
                                       ge_count, ctrl_raw, ctrl_norm);
     if (c->timed_trait) cudaEventRecord(c->ev[3], c->stream);
     return rc;
+}
+
+// ---- pipelined scoring: submit trait i + 1 while trait i finishes ------------------------------------
+// The inputs are copied into pinned memory (so their upload does not wait for the stream) and the results
+// are downloaded into pinned memory behind an event; nothing here blocks on the GPU.  Two slots.
+static int pin_reserve(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    SCDRS_CUDA(cudaHostAlloc(p, bytes + bytes / 8, cudaHostAllocDefault));
+    *cap = bytes + bytes / 8;
+    return 0;
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                             const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
+                             const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
+                             int32_t want_ctrl_raw, int32_t want_ctrl_norm, int32_t* slot_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(slot_out != nullptr && trait_genes && trait_gw && n_ctrl >= 0 && n_s >= 0 && n_s_ctrl >= 0, "null pointer");
+    SCDRS_CHECK(n_ctrl == 0 || n_s_ctrl == 0 || (ctrl_genes && ctrl_gw), "null gene-set arrays");
+    const int id = c->next_slot;
+    scdrs_ctx::Slot& sl = c->slot[id];
+    SCDRS_CHECK(!sl.busy, "both scoring slots are in flight: collect one first");
+    const int64_t n = c->n_cell;
+    // pinned input: [trait_genes | ctrl_genes | trait_gw | ctrl_gw]
+    const size_t o_tg = 0, o_cg = align16((size_t)n_s * 4), o_tw = o_cg + align16((size_t)n_ctrl * n_s_ctrl * 4),
+                 o_cw = o_tw + align16((size_t)n_s * 8), in_bytes = o_cw + align16((size_t)n_s_ctrl * 8);
+    SCDRS_TRY(pin_reserve(&sl.pin_in, &sl.in_cap, in_bytes));
+    char* in = static_cast<char*>(sl.pin_in);
+    memcpy(in + o_tg, trait_genes, (size_t)n_s * 4);
+    if (n_ctrl > 0 && n_s_ctrl > 0) {
+        memcpy(in + o_cg, ctrl_genes, (size_t)n_ctrl * n_s_ctrl * 4);
+        memcpy(in + o_cw, ctrl_gw, (size_t)n_s_ctrl * 8);
+    }
+    memcpy(in + o_tw, trait_gw, (size_t)n_s * 8);
+    // pinned output: [raw f64 | ge i64 | norm f32 | mc i32 | ctrl_raw f32 | ctrl_norm f32]
+    const size_t mat = (size_t)n * n_ctrl * 4;
+    const size_t out_bytes = align16((size_t)n * 8) * 2 + align16((size_t)n * 4) * 2 + (want_ctrl_raw ? align16(mat) : 0) +
+                             (want_ctrl_norm ? align16(mat) : 0);
+    SCDRS_TRY(pin_reserve(&sl.pin_out, &sl.out_cap, out_bytes));
+    if (!sl.done) SCDRS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    char* out = static_cast<char*>(sl.pin_out);
+    double* raw = reinterpret_cast<double*>(out);
+    int64_t* ge = reinterpret_cast<int64_t*>(out + align16((size_t)n * 8));
+    float* norm = reinterpret_cast<float*>(out + 2 * align16((size_t)n * 8));
+    int32_t* mc = reinterpret_cast<int32_t*>(out + 2 * align16((size_t)n * 8) + align16((size_t)n * 4));
+    char* tail = out + 2 * align16((size_t)n * 8) + 2 * align16((size_t)n * 4);
+    float* craw = want_ctrl_raw ? reinterpret_cast<float*>(tail) : nullptr;
+    float* cnorm = want_ctrl_norm ? reinterpret_cast<float*>(tail + (want_ctrl_raw ? align16(mat) : 0)) : nullptr;
+    c->finish_async = true;
+    const int rc = scdrs_score_trait(c, n_ctrl, n_s, n_s_ctrl, reinterpret_cast<const int32_t*>(in + o_tg),
+                                     reinterpret_cast<const double*>(in + o_tw), reinterpret_cast<const int32_t*>(in + o_cg),
+                                     reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, raw, norm, mc,
+                                     ge, craw, cnorm);
+    c->finish_async = false;
+    if (rc) return rc;
+    SCDRS_CUDA(cudaEventRecord(sl.done, c->stream));
+    sl.busy = true;
+    sl.n_ctrl = n_ctrl;
+    sl.ctrl_raw = want_ctrl_raw != 0;
+    sl.ctrl_norm = want_ctrl_norm != 0;
+    c->next_slot = id ^ 1;
+    *slot_out = id;
+    return 0;
+}
+
+int scdrs_score_trait_collect(scdrs_ctx* c, int32_t slot, double* raw_score, float* norm_score, int32_t* mc_count,
+                              int64_t* ge_count, float* ctrl_raw, float* ctrl_norm) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+    scdrs_ctx::Slot& sl = c->slot[slot];
+    SCDRS_CHECK(sl.busy, "nothing was submitted to this slot");
+    SCDRS_CHECK((ctrl_raw == nullptr || sl.ctrl_raw) && (ctrl_norm == nullptr || sl.ctrl_norm),
+                "control scores were not requested at submit");
+    SCDRS_CUDA(cudaEventSynchronize(sl.done));
+    sl.busy = false;
+    const int64_t n = c->n_cell;
+    const size_t mat = (size_t)n * sl.n_ctrl * 4;
+    const char* out = static_cast<const char*>(sl.pin_out);
+    if (raw_score) memcpy(raw_score, out, (size_t)n * 8);
+    if (ge_count) memcpy(ge_count, out + align16((size_t)n * 8), (size_t)n * 8);
+    if (norm_score) memcpy(norm_score, out + 2 * align16((size_t)n * 8), (size_t)n * 4);
+    if (mc_count) memcpy(mc_count, out + 2 * align16((size_t)n * 8) + align16((size_t)n * 4), (size_t)n * 4);
+    const char* tail = out + 2 * align16((size_t)n * 8) + 2 * align16((size_t)n * 4);
+    if (ctrl_raw) memcpy(ctrl_raw, tail, mat);
+    if (ctrl_norm) memcpy(ctrl_norm, tail + (sl.ctrl_raw ? align16(mat) : 0), mat);
+    return 0;
 }
 
 // ---- stand-alone helpers --------------------------------------------------------------------------

@@ -75,6 +75,20 @@ struct scdrs_ctx {
     int32_t k = 0;  // number of covariates (0 = normal mode)
     scdrs::DevBuf cov_mat, cov_beta, gene_mean;
 
+    // pipelined scoring (scdrs_score_trait_submit / _collect): two slots of pinned host staging
+    struct Slot {
+        void* pin_in = nullptr;
+        size_t in_cap = 0;
+        void* pin_out = nullptr;
+        size_t out_cap = 0;
+        cudaEvent_t done = nullptr;
+        bool busy = false;
+        int32_t n_ctrl = 0;
+        bool ctrl_raw = false, ctrl_norm = false;
+    } slot[2];
+    int next_slot = 0;
+    bool finish_async = false;      // scdrs_trait_finish leaves the final stream synchronisation to the caller
+
     // downstream analyses (downstream.cu): the score matrix of one trait, [ds_n x ds_ncol] fp64 row-major
     scdrs::DevBuf ds_S, ds_tmp, ds_pos, ds_M, ds_keys, ds_vals, ds_off, ds_ref, ds_chunk, ds_part;
     int64_t ds_n = 0;

@@ -428,6 +428,14 @@ def score_traits(
         else:
             score_one = ctx.score_trait
         pending = []          # (trait, future of the result frame): frames are built off the critical path
+        in_flight = None      # (trait, ticket) submitted to the GPU and not collected yet (single GPU)
+
+        def collect(item):
+            t_prev, ticket = item
+            out_prev = ctx.score_trait_collect(ticket)
+            pending.append((t_prev, frame_pool.submit(_result_frame, adata, out_prev, n_ctrl, return_ctrl_raw_score,
+                                                      return_ctrl_norm_score)))
+            drain(2)
 
         def drain(limit):
             while len(pending) > limit:
@@ -438,20 +446,45 @@ def score_traits(
                 else:
                     on_result(t_done, df_done)
 
-        for i_t, t in enumerate(traits):
-            if share_draws:
-                owner = i_t % world
-                prep = broadcast_prep(futs.pop(t).result() if owner == rank else None, owner, n_ctrl,
-                                      len(dict_gs[t][0]), dev)
-            else:
-                prep = futs.pop(t).result()
-            out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
-                            weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
-                            want_ctrl_norm=return_ctrl_norm_score)
-            pending.append((t, frame_pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
-                                           return_ctrl_norm_score)))
-            drain(2)
-        drain(0)
+        def run_all():
+            nonlocal in_flight
+            for i_t, t in enumerate(traits):
+                if share_draws:
+                    owner = i_t % world
+                    prep = broadcast_prep(futs.pop(t).result() if owner == rank else None, owner, n_ctrl,
+                                          len(dict_gs[t][0]), dev)
+                else:
+                    prep = futs.pop(t).result()
+                if not sharded:
+                    # the next trait is queued behind the current one before the current one's results are
+                    # fetched: the GPU never waits for the host between traits
+                    ticket = ctx.score_trait_submit(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"],
+                                                    prep["ctrl_gw"], weight_opt, use_ratio,
+                                                    want_ctrl_raw=return_ctrl_raw_score,
+                                                    want_ctrl_norm=return_ctrl_norm_score)
+                    if in_flight is not None:
+                        collect(in_flight)
+                    in_flight = (t, ticket)
+                    continue
+                out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
+                                weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
+                                want_ctrl_norm=return_ctrl_norm_score)
+                pending.append((t, frame_pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
+                                                     return_ctrl_norm_score)))
+                drain(2)
+            if in_flight is not None:
+                last, in_flight = in_flight, None
+                collect(last)
+            drain(0)
+
+        try:
+            run_all()
+        finally:
+            if in_flight is not None:       # an error above: free the slot, drop its results
+                try:
+                    ctx.score_trait_collect(in_flight[1])
+                except Exception:
+                    pass
     np.random.seed(random_seed)
     return results if on_result is None else traits
 

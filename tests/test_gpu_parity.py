@@ -766,3 +766,37 @@ def test_load_h5ad_toy_file_device_path(native_lib):
     assert "n_genes" in adata.obs and "n_cells" in adata.var and "n_counts" in adata.obs
     assert np.allclose(np.expm1(adata.X.toarray()).sum(axis=1), 1e4, rtol=1e-4)
     assert (adata.obs["n_genes"] >= 500).all()
+
+
+def test_pipelined_submit_collect_equals_blocking_call(native_lib):
+    """scdrs_score_trait_submit / _collect (two traits in flight, pinned staging) against scdrs_score_trait:
+    identical bytes, control matrices included; a third submit without a collect is refused."""
+    import scdrs_b200
+    from scdrs_b200 import _device, method, synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(700, 2000, density=0.1, seed=5)
+    orc.preprocess(adata, cov=cov, loess_impl=loess)
+    traits = synth.make_traits(adata.var_names, 3, 100, weighted=True, seed=9)
+    state = _device.get_state(adata)
+    ctx = state.ensure_matrix(adata)
+    state.ensure_cov(adata, True)
+    tab = method._gene_table(adata, state)
+    ctx.set_gene_stats(tab.var, tab.var_tech)
+    preps = [method._prepare_trait(adata, state, g, w, "mean_var", 60, 200, 0) for g, w in traits.values()]
+    args = lambda p: (p["trait_cols"], p["trait_gw"], p["ctrl_cols"], p["ctrl_gw"], "vs", True)   # noqa: E731
+    want = [ctx.score_trait(*args(p), want_ctrl_raw=True, want_ctrl_norm=True) for p in preps]
+    t0 = ctx.score_trait_submit(*args(preps[0]), want_ctrl_raw=True, want_ctrl_norm=True)
+    t1 = ctx.score_trait_submit(*args(preps[1]), want_ctrl_raw=True, want_ctrl_norm=True)
+    with pytest.raises(RuntimeError, match="slots"):
+        ctx.score_trait_submit(*args(preps[2]))
+    got0 = ctx.score_trait_collect(t0)
+    t2 = ctx.score_trait_submit(*args(preps[2]), want_ctrl_norm=True)
+    got = [got0, ctx.score_trait_collect(t1), ctx.score_trait_collect(t2)]
+    for g, w_ in zip(got, want):
+        for key in ("raw_score", "norm_score", "mc_count", "ge_count", "ctrl_norm"):
+            assert np.array_equal(g[key], w_[key], equal_nan=True), key
+    assert np.array_equal(got[0]["ctrl_raw"], want[0]["ctrl_raw"], equal_nan=True) and got[2]["ctrl_raw"] is None
+    with pytest.raises(RuntimeError, match="nothing was submitted"):
+        ctx.score_trait_collect(t0)
+    scdrs_b200.clear_device_cache()
