@@ -138,6 +138,18 @@ int scdrs_score_trait_submit(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_
 int scdrs_score_trait_collect(scdrs_ctx* ctx, int32_t slot, double* raw_score, float* norm_score,
                               int32_t* mc_count, int64_t* ge_count, float* ctrl_raw, float* ctrl_norm);
 
+/* The same split for the phase-by-phase (multi-GPU) driver: phase 1 with the control sets already in
+ * device memory (dev_ctrl_genes[n_ctrl x n_s_ctrl], e.g. the receive buffer of a broadcast; the small
+ * host arrays are staged through pinned memory), and phase 5 into pinned memory behind an event --
+ * collect with scdrs_score_trait_collect(slot). */
+int scdrs_trait_raw_dev(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
+                        const int32_t* trait_genes, const double* trait_gw,
+                        const int32_t* dev_ctrl_genes, const double* ctrl_gw, int32_t weight_opt,
+                        int32_t use_var_ratio, double* dev_colsum_out);
+int scdrs_trait_finish_submit(scdrs_ctx* ctx, const unsigned long long* dev_hist_all,
+                              int64_t n_query_all, int64_t query_offset, int64_t n_null_total,
+                              int32_t want_ctrl_raw, int32_t want_ctrl_norm, int32_t* slot_out);
+
 /* ---- the reference's helper functions as stand-alone calls (host buffers) ------------------ */
 /* _compute_raw_score (scdrs/method.py:377-400) for n_set explicit gene sets with FINAL weights
  * w[n_set x n_s] (already normalised); raw_out[n_cell x n_set] f64. */

@@ -55,6 +55,10 @@ SIGNATURES = {
                                            C.POINTER(C.c_int32)]),
     "scdrs_score_trait_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]),
+    "scdrs_trait_raw_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "scdrs_trait_finish_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_int32)]),
     "scdrs_compute_raw_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_correct_background": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -276,6 +280,25 @@ class Context:
         check(self._L.scdrs_trait_raw(self._h, ctrl_genes.shape[0], trait_genes.shape[0], ctrl_genes.shape[1], ptr(trait_genes),
                                       ptr(trait_gw), ptr(ctrl_genes), ptr(ctrl_gw), WEIGHT_OPT[weight_opt],
                                       int(bool(use_var_ratio)), int(d_colsum)))
+
+    def trait_raw_dev(self, trait_genes, trait_gw, d_ctrl_genes, n_ctrl, n_sc, ctrl_gw, weight_opt, use_var_ratio,
+                      d_colsum):
+        """Phase 1 with the control sets [n_ctrl x n_sc] int32 already in device memory."""
+        trait_genes = as_c(trait_genes, np.int32)
+        trait_gw, ctrl_gw = as_c(trait_gw, np.float64), as_c(ctrl_gw, np.float64)
+        assert ctrl_gw.shape[0] == n_sc
+        check(self._L.scdrs_trait_raw_dev(self._h, int(n_ctrl), trait_genes.shape[0], int(n_sc), ptr(trait_genes),
+                                          ptr(trait_gw), int(d_ctrl_genes), ptr(ctrl_gw), WEIGHT_OPT[weight_opt],
+                                          int(bool(use_var_ratio)), int(d_colsum)))
+
+    def trait_finish_submit(self, d_hist_all, n_query_all, query_offset, n_null_total, n_ctrl,
+                            want_ctrl_raw=False, want_ctrl_norm=False):
+        """Phase 5 without waiting; returns a ticket for ``score_trait_collect``."""
+        slot = C.c_int32(-1)
+        check(self._L.scdrs_trait_finish_submit(self._h, int(d_hist_all), int(n_query_all), int(query_offset),
+                                                int(n_null_total), int(bool(want_ctrl_raw)),
+                                                int(bool(want_ctrl_norm)), C.byref(slot)))
+        return (slot.value, n_ctrl, bool(want_ctrl_raw), bool(want_ctrl_norm))
 
     def trait_rowstats(self, d_colsum, n_cell_total, d_colsum2, d_colmin):
         check(self._L.scdrs_trait_rowstats(self._h, int(d_colsum), int(n_cell_total), int(d_colsum2), int(d_colmin)))

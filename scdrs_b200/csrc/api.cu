@@ -517,6 +517,29 @@ static int pin_reserve(void** p, size_t* cap, size_t bytes) {
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// pinned result block of a slot: [raw f64 | ge i64 | norm f32 | mc i32 | ctrl_raw f32 | ctrl_norm f32]
+struct SlotOut {
+    double* raw;
+    int64_t* ge;
+    float* norm;
+    int32_t* mc;
+    float *craw, *cnorm;
+    size_t bytes;
+};
+static SlotOut slot_layout(char* out, int64_t n, int32_t n_ctrl, bool want_raw, bool want_norm) {
+    const size_t mat = align16((size_t)n * n_ctrl * 4), a8 = align16((size_t)n * 8), a4 = align16((size_t)n * 4);
+    SlotOut o;
+    o.raw = reinterpret_cast<double*>(out);
+    o.ge = reinterpret_cast<int64_t*>(out + a8);
+    o.norm = reinterpret_cast<float*>(out + 2 * a8);
+    o.mc = reinterpret_cast<int32_t*>(out + 2 * a8 + a4);
+    char* tail = out + 2 * a8 + 2 * a4;
+    o.craw = want_raw ? reinterpret_cast<float*>(tail) : nullptr;
+    o.cnorm = want_norm ? reinterpret_cast<float*>(tail + (want_raw ? mat : 0)) : nullptr;
+    o.bytes = 2 * a8 + 2 * a4 + (want_raw ? mat : 0) + (want_norm ? mat : 0);
+    return o;
+}
+
 int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                              const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
                              const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
@@ -539,25 +562,15 @@ int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t 
         memcpy(in + o_cw, ctrl_gw, (size_t)n_s_ctrl * 8);
     }
     memcpy(in + o_tw, trait_gw, (size_t)n_s * 8);
-    // pinned output: [raw f64 | ge i64 | norm f32 | mc i32 | ctrl_raw f32 | ctrl_norm f32]
-    const size_t mat = (size_t)n * n_ctrl * 4;
-    const size_t out_bytes = align16((size_t)n * 8) * 2 + align16((size_t)n * 4) * 2 + (want_ctrl_raw ? align16(mat) : 0) +
-                             (want_ctrl_norm ? align16(mat) : 0);
-    SCDRS_TRY(pin_reserve(&sl.pin_out, &sl.out_cap, out_bytes));
+    SlotOut o = slot_layout(nullptr, n, n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
+    SCDRS_TRY(pin_reserve(&sl.pin_out, &sl.out_cap, o.bytes));
     if (!sl.done) SCDRS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-    char* out = static_cast<char*>(sl.pin_out);
-    double* raw = reinterpret_cast<double*>(out);
-    int64_t* ge = reinterpret_cast<int64_t*>(out + align16((size_t)n * 8));
-    float* norm = reinterpret_cast<float*>(out + 2 * align16((size_t)n * 8));
-    int32_t* mc = reinterpret_cast<int32_t*>(out + 2 * align16((size_t)n * 8) + align16((size_t)n * 4));
-    char* tail = out + 2 * align16((size_t)n * 8) + 2 * align16((size_t)n * 4);
-    float* craw = want_ctrl_raw ? reinterpret_cast<float*>(tail) : nullptr;
-    float* cnorm = want_ctrl_norm ? reinterpret_cast<float*>(tail + (want_ctrl_raw ? align16(mat) : 0)) : nullptr;
+    o = slot_layout(static_cast<char*>(sl.pin_out), n, n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
     c->finish_async = true;
     const int rc = scdrs_score_trait(c, n_ctrl, n_s, n_s_ctrl, reinterpret_cast<const int32_t*>(in + o_tg),
                                      reinterpret_cast<const double*>(in + o_tw), reinterpret_cast<const int32_t*>(in + o_cg),
-                                     reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, raw, norm, mc,
-                                     ge, craw, cnorm);
+                                     reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, o.raw, o.norm,
+                                     o.mc, o.ge, o.craw, o.cnorm);
     c->finish_async = false;
     if (rc) return rc;
     SCDRS_CUDA(cudaEventRecord(sl.done, c->stream));
@@ -582,14 +595,67 @@ int scdrs_score_trait_collect(scdrs_ctx* c, int32_t slot, double* raw_score, flo
     sl.busy = false;
     const int64_t n = c->n_cell;
     const size_t mat = (size_t)n * sl.n_ctrl * 4;
-    const char* out = static_cast<const char*>(sl.pin_out);
-    if (raw_score) memcpy(raw_score, out, (size_t)n * 8);
-    if (ge_count) memcpy(ge_count, out + align16((size_t)n * 8), (size_t)n * 8);
-    if (norm_score) memcpy(norm_score, out + 2 * align16((size_t)n * 8), (size_t)n * 4);
-    if (mc_count) memcpy(mc_count, out + 2 * align16((size_t)n * 8) + align16((size_t)n * 4), (size_t)n * 4);
-    const char* tail = out + 2 * align16((size_t)n * 8) + 2 * align16((size_t)n * 4);
-    if (ctrl_raw) memcpy(ctrl_raw, tail, mat);
-    if (ctrl_norm) memcpy(ctrl_norm, tail + (sl.ctrl_raw ? align16(mat) : 0), mat);
+    const SlotOut o = slot_layout(static_cast<char*>(sl.pin_out), n, sl.n_ctrl, sl.ctrl_raw, sl.ctrl_norm);
+    if (raw_score) memcpy(raw_score, o.raw, (size_t)n * 8);
+    if (ge_count) memcpy(ge_count, o.ge, (size_t)n * 8);
+    if (norm_score) memcpy(norm_score, o.norm, (size_t)n * 4);
+    if (mc_count) memcpy(mc_count, o.mc, (size_t)n * 4);
+    if (ctrl_raw) memcpy(ctrl_raw, o.craw, mat);
+    if (ctrl_norm) memcpy(ctrl_norm, o.cnorm, mat);
+    return 0;
+}
+
+// Phase-level halves for the multi-GPU driver: phase 1 with the control sets already on the device (they
+// arrive there by broadcast) and the small host arrays staged through the slot's pinned block, and phase 5
+// into the slot's pinned result block behind an event (collected with scdrs_score_trait_collect).
+int scdrs_trait_raw_dev(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl, const int32_t* trait_genes,
+                        const double* trait_gw, const int32_t* dev_ctrl_genes, const double* ctrl_gw,
+                        int32_t weight_opt, int32_t use_var_ratio, double* dev_colsum_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(trait_genes && trait_gw && n_ctrl >= 0 && n_s >= 0 && n_s_ctrl >= 0, "null pointer");
+    SCDRS_CHECK(n_ctrl == 0 || n_s_ctrl == 0 || (dev_ctrl_genes && ctrl_gw), "null gene-set arrays");
+    SCDRS_CHECK(dev_colsum_out != nullptr, "null output");
+    scdrs_ctx::Slot& sl = c->slot[c->next_slot];
+    SCDRS_CHECK(!sl.busy, "both scoring slots are in flight: collect one first");
+    const size_t o_tw = align16((size_t)n_s * 4), o_cw = o_tw + align16((size_t)n_s * 8),
+                 in_bytes = o_cw + align16((size_t)n_s_ctrl * 8);
+    SCDRS_TRY(pin_reserve(&sl.pin_in, &sl.in_cap, in_bytes));
+    char* in = static_cast<char*>(sl.pin_in);
+    memcpy(in, trait_genes, (size_t)n_s * 4);
+    memcpy(in + o_tw, trait_gw, (size_t)n_s * 8);
+    if (n_s_ctrl > 0 && ctrl_gw) memcpy(in + o_cw, ctrl_gw, (size_t)n_s_ctrl * 8);
+    SCDRS_TRY(trait_prepare(c, n_ctrl, n_s, n_s_ctrl, reinterpret_cast<const int32_t*>(in),
+                            reinterpret_cast<const double*>(in + o_tw), dev_ctrl_genes,
+                            reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, true));
+    SCDRS_TRY(spmm_score(c));
+    return bg_colsum(c, dev_colsum_out);
+}
+
+int scdrs_trait_finish_submit(scdrs_ctx* c, const unsigned long long* dev_hist_all, int64_t n_query_all,
+                              int64_t query_offset, int64_t n_null_total, int32_t want_ctrl_raw,
+                              int32_t want_ctrl_norm, int32_t* slot_out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(slot_out != nullptr, "null pointer");
+    const int id = c->next_slot;
+    scdrs_ctx::Slot& sl = c->slot[id];
+    SCDRS_CHECK(!sl.busy, "both scoring slots are in flight: collect one first");
+    const int64_t n = c->n_cell;
+    SlotOut o = slot_layout(nullptr, n, c->n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
+    SCDRS_TRY(pin_reserve(&sl.pin_out, &sl.out_cap, o.bytes));
+    if (!sl.done) SCDRS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    o = slot_layout(static_cast<char*>(sl.pin_out), n, c->n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
+    c->finish_async = true;
+    const int rc = scdrs_trait_finish(c, dev_hist_all, n_query_all, query_offset, n_null_total, o.raw, o.norm, o.mc,
+                                      o.ge, o.craw, o.cnorm);
+    c->finish_async = false;
+    if (rc) return rc;
+    SCDRS_CUDA(cudaEventRecord(sl.done, c->stream));
+    sl.busy = true;
+    sl.n_ctrl = c->n_ctrl;
+    sl.ctrl_raw = want_ctrl_raw != 0;
+    sl.ctrl_norm = want_ctrl_norm != 0;
+    c->next_slot = id ^ 1;
+    *slot_out = id;
     return 0;
 }
 

@@ -138,7 +138,7 @@ namespace scdrs {
 // ---- spmm_score.cu ------------------------------------------------------------------------
 int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                   const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
-                  const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio);
+                  const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio, bool ctrl_on_device = false);
 int explicit_prepare(scdrs_ctx* c, int32_t n_set, int32_t n_s, const int32_t* genes,
                      const double* w);
 int spmm_score(scdrs_ctx* c);

@@ -371,7 +371,8 @@ w_layout_greedy_kernel(int n_gene, const uint32_t* __restrict__ w_ptr, const uin
 }
 
 static int upload_sets(scdrs_ctx* c, const int32_t* trait_genes, const int32_t* ctrl_genes,
-                       const double* gw_trait, const double* gw_ctrl, const double* explicit_w) {
+                       const double* gw_trait, const double* gw_ctrl, const double* explicit_w,
+                       bool ctrl_on_device = false) {
     const int32_t n_s = c->n_s, n_sc = c->n_sc;
     const size_t n_entry = (size_t)n_s + (size_t)c->n_ctrl * n_sc;
     SCDRS_TRY(c->set_genes.reserve(n_entry * sizeof(int32_t)));
@@ -382,7 +383,8 @@ static int upload_sets(scdrs_ctx* c, const int32_t* trait_genes, const int32_t* 
                                    cudaMemcpyHostToDevice, c->stream));
         if (n_entry > (size_t)n_s)
             SCDRS_CUDA(cudaMemcpyAsync(c->set_genes.as<int32_t>() + n_s, ctrl_genes,
-                                       (n_entry - n_s) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                       (n_entry - n_s) * sizeof(int32_t),
+                                       ctrl_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                        c->stream));
         SCDRS_CUDA(cudaMemcpyAsync(c->set_gw.p, gw_trait, n_s * sizeof(double),
                                    cudaMemcpyHostToDevice, c->stream));
@@ -533,7 +535,7 @@ static int set_shape(scdrs_ctx* c, int32_t ncol, int32_t n_s, int32_t n_sc) {
 
 int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                   const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
-                  const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio) {
+                  const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio, bool ctrl_on_device) {
     SCDRS_CHECK(n_ctrl >= 0, "n_ctrl < 0");
     SCDRS_CHECK(weight_opt >= 0 && weight_opt <= 2, "illegal weight_opt %d", weight_opt);
     SCDRS_CHECK(weight_opt == SCDRS_WEIGHT_UNIFORM || c->have_stats,
@@ -548,7 +550,7 @@ int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
     double gw_absmax = 0.0;
     for (int i = 0; i < n_s; ++i) gw_absmax = fabs(trait_gw[i]) > gw_absmax ? fabs(trait_gw[i]) : gw_absmax;
     for (int i = 0; i < n_s_ctrl && n_ctrl > 0; ++i) gw_absmax = fabs(ctrl_gw[i]) > gw_absmax ? fabs(ctrl_gw[i]) : gw_absmax;
-    SCDRS_TRY(upload_sets(c, trait_genes, ctrl_genes, trait_gw, ctrl_gw, nullptr));
+    SCDRS_TRY(upload_sets(c, trait_genes, ctrl_genes, trait_gw, ctrl_gw, nullptr, ctrl_on_device));
     return build_w(c, weight_opt, use_var_ratio, false, binary, gw_absmax);
 }
 

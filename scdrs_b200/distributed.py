@@ -37,7 +37,12 @@ class CudaPhases:
         ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
 
     def raw(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio, colsum):
-        self.ctx.trait_raw(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio, colsum.data_ptr())
+        if isinstance(ctrl_genes, torch.Tensor):      # already on the device (the receive buffer of a broadcast)
+            assert ctrl_genes.is_cuda and ctrl_genes.dtype == torch.int32 and ctrl_genes.is_contiguous()
+            self.ctx.trait_raw_dev(trait_genes, trait_gw, ctrl_genes.data_ptr(), ctrl_genes.shape[0], ctrl_genes.shape[1],
+                                   ctrl_gw, weight_opt, use_ratio, colsum.data_ptr())
+        else:
+            self.ctx.trait_raw(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio, colsum.data_ptr())
 
     def rowstats(self, colsum, n_cell_total, col2, colmin):
         self.ctx.trait_rowstats(colsum.data_ptr(), n_cell_total, col2.data_ptr(), colmin.data_ptr())
@@ -51,6 +56,14 @@ class CudaPhases:
     def finish(self, hist, n_query_all, offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm):
         return self.ctx.trait_finish(hist.data_ptr(), n_query_all, offset, n_null_total, n_ctrl,
                                      want_ctrl_raw, want_ctrl_norm)
+
+
+    def finish_submit(self, hist, n_query_all, offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm):
+        return self.ctx.trait_finish_submit(hist.data_ptr(), n_query_all, offset, n_null_total, n_ctrl,
+                                            want_ctrl_raw, want_ctrl_norm)
+
+    def collect(self, ticket):
+        return self.ctx.score_trait_collect(ticket)
 
 
 class ShardedScorer:
@@ -103,7 +116,28 @@ class ShardedScorer:
               want_ctrl_raw=False, want_ctrl_norm=False):
         """Returns the dict of ``Context.score_trait`` for this rank's cells, with pooled-null
         counts over ALL ranks' cells (``n_null_total`` = total cells x n_ctrl)."""
-        ctrl_genes = np.asarray(ctrl_genes)
+        hist, n_ctrl = self._phases_1_to_4(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio)
+        n_null_total = self.n_total * n_ctrl
+        out = self.p.finish(hist, self.n_total, self.offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm)
+        out["n_null_total"] = n_null_total
+        return out
+
+    def submit(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio,
+               want_ctrl_raw=False, want_ctrl_norm=False):
+        """``score`` without waiting for the GPU: everything (collectives included) is queued on the stream and
+        the results land in pinned memory; ``collect(ticket)`` returns them.  At most two tickets outstanding."""
+        hist, n_ctrl = self._phases_1_to_4(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio)
+        return self.p.finish_submit(hist, self.n_total, self.offset, self.n_total * n_ctrl, n_ctrl,
+                                    want_ctrl_raw, want_ctrl_norm)
+
+    def collect(self, ticket):
+        out = self.p.collect(ticket)
+        out["n_null_total"] = self.n_total * ticket[1]
+        return out
+
+    def _phases_1_to_4(self, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio):
+        if not isinstance(ctrl_genes, torch.Tensor):
+            ctrl_genes = np.asarray(ctrl_genes)
         n_ctrl = ctrl_genes.shape[0]
         ncol = n_ctrl + 1
         colsum = self._tensor("colsum", ncol, torch.float64)
@@ -124,10 +158,31 @@ class ShardedScorer:
         self.p.count(q_all, hist)
         if self.world > 1:
             dist.all_reduce(hist)
-        n_null_total = self.n_total * n_ctrl
-        out = self.p.finish(hist, self.n_total, self.offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm)
-        out["n_null_total"] = n_null_total
-        return out
+        return hist, n_ctrl
+
+
+class DrawBroadcaster:
+    """Ships the control sets of one trait (the only random part of ``method._prepare_trait``) from the rank that
+    drew them into a device buffer on every rank, without a host round trip on the receivers: pinned staging on
+    the owner, NCCL broadcast on the stream the kernels run on.  Two buffers alternate (two traits in flight)."""
+
+    def __init__(self, device, cap):
+        self.device = device
+        self.dev = [torch.empty(cap, dtype=torch.int32, device=device) for _ in range(2)]
+        self.pin = [torch.empty(cap, dtype=torch.int32, pin_memory=(device.type == "cuda")) for _ in range(2)]
+        self.k = 0
+
+    def ship(self, ctrl_cols, src, n_ctrl, n_sc):
+        """ctrl_cols: the drawn sets on rank ``src`` (None elsewhere).  Returns an int32 [n_ctrl, n_sc] device view
+        that stays valid until the call after next."""
+        k, self.k = self.k, self.k ^ 1
+        m = n_ctrl * n_sc
+        buf = self.dev[k][:m]
+        if ctrl_cols is not None:
+            self.pin[k][:m].copy_(torch.from_numpy(np.ascontiguousarray(ctrl_cols, dtype=np.int32).reshape(-1)))
+            buf.copy_(self.pin[k][:m], non_blocking=True)
+        dist.broadcast(buf, src=src)
+        return buf.view(n_ctrl, n_sc)
 
 
 def broadcast_prep(prep, src, n_ctrl, n_s_max, device):

@@ -61,17 +61,24 @@ def _bins_for(df_gene, ctrl_match_key, n_genebin, cache=None):
     return cache[ck]
 
 
-def _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=None):
-    """Control sets as integer positions; see include/scdrs_b200.h:scdrs_select_ctrl.
-
-    trait_pos must be ordered by gene name.  Returns (ctrl_pos[n_ctrl, n_sc], ctrl_gw[n_sc]).
-    """
+def _ctrl_layout(bins, trait_pos, trait_gw):
+    """What is known about the control sets before any draw: trait genes per bin and the weight every control
+    position inherits.  Returns (ntrait[n_bin] int32, ctrl_gw[n_sc])."""
     tcode = bins.code[trait_pos]
     in_bin = tcode >= 0
     ntrait = np.bincount(tcode[in_bin], minlength=bins.n_bin).astype(np.int32)
     # the p-th control gene of a bin inherits the weight of the p-th trait gene (by name) of that bin
     order = np.argsort(tcode[in_bin], kind="stable")
     ctrl_gw = np.asarray(trait_gw, dtype=np.float64)[in_bin][order]
+    return ntrait, ctrl_gw
+
+
+def _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=None):
+    """Control sets as integer positions; see include/scdrs_b200.h:scdrs_select_ctrl.
+
+    trait_pos must be ordered by gene name.  Returns (ctrl_pos[n_ctrl, n_sc], ctrl_gw[n_sc]).
+    """
+    ntrait, ctrl_gw = _ctrl_layout(bins, trait_pos, trait_gw)
     genes = bins.bin_pos if col_of is None else col_of[bins.bin_pos]
     ctrl = _native.select_ctrl(random_seed, bins.bin_ptr, genes, ntrait, n_ctrl, int(ntrait.sum()))
     return ctrl, ctrl_gw
@@ -199,10 +206,11 @@ def _gene_table(adata, state):
 
 
 def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed,
-                   tab=None, bins=None):
+                   tab=None, bins=None, draw=True):
     """Host work of one trait: gene intersection (:146-159) and control draws (:168).
 
-    ``tab`` / ``bins`` let a multi-trait caller compute the per-dataset tables once."""
+    ``tab`` / ``bins`` let a multi-trait caller compute the per-dataset tables once.  ``draw=False`` leaves the
+    draws out (``ctrl_cols`` is None): what a rank needs when another rank draws for it."""
     if tab is None:
         tab = _gene_table(adata, state)
     gene_list = list(gene_list)
@@ -213,7 +221,10 @@ def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl,
     trait_gw = np.array([dic_gene_weight[x] for x in genes], dtype=np.float64)
     if bins is None:
         bins = _bins_for(tab.df_gene, ctrl_match_key, n_genebin, state.bins_cache if state is not None else None)
-    ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=tab.col_of)
+    if draw:
+        ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=tab.col_of)
+    else:
+        ctrl_cols, ctrl_gw = None, _ctrl_layout(bins, trait_pos, trait_gw)[1]
     return dict(genes=genes, trait_cols=tab.col_of[trait_pos].astype(np.int32), trait_gw=trait_gw,
                 ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=tab.var, var_tech=tab.var_tech)
 
@@ -411,20 +422,20 @@ def score_traits(
         share_draws = world > 1 and os.environ.get("SCDRS_B200_LOCAL_DRAWS", "0") != "1"
         futs = {}
         for i_t, t in enumerate(traits):
-            if share_draws and i_t % world != rank:
-                continue
             g, w = dict_gs[t]
             futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
-                                  tab, bins)
+                                  tab, bins, not (share_draws and i_t % world != rank))
         ctx = state.ensure_matrix(adata)
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
         if sharded:
-            from .distributed import CudaPhases, ShardedScorer, broadcast_prep
+            from .distributed import CudaPhases, DrawBroadcaster, ShardedScorer
 
             dev = torch.device("cuda", torch.cuda.current_device())
             scorer = ShardedScorer(CudaPhases(ctx, dev), dev)
             score_one = scorer.score
+            if share_draws:
+                shipper = DrawBroadcaster(dev, n_ctrl * max(len(dict_gs[t][0]) for t in traits))
         else:
             score_one = ctx.score_trait
         pending = []          # (trait, future of the result frame): frames are built off the critical path
@@ -432,7 +443,7 @@ def score_traits(
 
         def collect(item):
             t_prev, ticket = item
-            out_prev = ctx.score_trait_collect(ticket)
+            out_prev = scorer.collect(ticket) if sharded else ctx.score_trait_collect(ticket)
             pending.append((t_prev, frame_pool.submit(_result_frame, adata, out_prev, n_ctrl, return_ctrl_raw_score,
                                                       return_ctrl_norm_score)))
             drain(2)
@@ -449,12 +460,18 @@ def score_traits(
         def run_all():
             nonlocal in_flight
             for i_t, t in enumerate(traits):
+                prep = futs.pop(t).result()
                 if share_draws:
-                    owner = i_t % world
-                    prep = broadcast_prep(futs.pop(t).result() if owner == rank else None, owner, n_ctrl,
-                                          len(dict_gs[t][0]), dev)
-                else:
-                    prep = futs.pop(t).result()
+                    # the drawn sets travel owner -> pinned -> device -> NCCL broadcast and are consumed on the
+                    # device; the other ranks computed everything else about the trait themselves
+                    d_ctrl = shipper.ship(prep["ctrl_cols"], i_t % world, n_ctrl, prep["ctrl_gw"].shape[0])
+                    ticket = scorer.submit(prep["trait_cols"], prep["trait_gw"], d_ctrl, prep["ctrl_gw"], weight_opt,
+                                           use_ratio, want_ctrl_raw=return_ctrl_raw_score,
+                                           want_ctrl_norm=return_ctrl_norm_score)
+                    if in_flight is not None:
+                        collect(in_flight)
+                    in_flight = (t, ticket)
+                    continue
                 if not sharded:
                     # the next trait is queued behind the current one before the current one's results are
                     # fetched: the GPU never waits for the host between traits

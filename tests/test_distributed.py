@@ -166,6 +166,22 @@ def _run_bcast(rank, world, port, out_dir):
             got = broadcast_prep(mine if rank == src else None, src, n_ctrl, n_s_max, torch.device("cpu"))
             for k, v in mine.items():                 # same generator on every rank: `mine` is the truth
                 assert got[k].dtype == v.dtype and np.array_equal(got[k], v), (rank, src, k)
+        # the product path: only the drawn sets travel (everything else is computed by every rank), straight
+        # into a device buffer; two buffers alternate, so a view stays valid until the call after next
+        from scdrs_b200.distributed import DrawBroadcaster
+
+        shipper = DrawBroadcaster(torch.device("cpu"), n_ctrl * n_s_max)
+        views, truths = [], []
+        for i in range(5):
+            src = i % world
+            rng = np.random.default_rng(200 + i)
+            n_sc = 25 + i
+            mine = rng.integers(0, 5000, (n_ctrl, n_sc)).astype(np.int32)
+            views.append(shipper.ship(mine if rank == src else None, src, n_ctrl, n_sc))
+            truths.append(mine)
+            assert np.array_equal(views[-1].numpy(), mine), (rank, i)
+            if i >= 1:
+                assert np.array_equal(views[-2].numpy(), truths[-2]), (rank, i, "previous view")
         open(os.path.join(out_dir, "bcast_ok_%d" % rank), "w").close()
     finally:
         dist.destroy_process_group()
