@@ -335,6 +335,8 @@ def main():
     scdrs_b200.set_default_device(local_rank)
     scdrs_b200.set_spmm_mode(args.spmm)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     adata, traits, info = build_workload(args, rank, device)
