@@ -282,7 +282,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "cell*trait/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def baseline_config_name(args, n_gpus):
@@ -312,8 +312,28 @@ def workload_config(args, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner, warnings of
+    worker processes) is sent to stderr, and the line itself goes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -335,8 +355,6 @@ def main():
     scdrs_b200.set_default_device(local_rank)
     scdrs_b200.set_spmm_mode(args.spmm)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     adata, traits, info = build_workload(args, rank, device)
@@ -535,7 +553,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "phases": phases, "setup": info,
             "device_ms_per_trait": 1e3 * wall / args.steps / len(names), "wall_s_check": wall_check,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
