@@ -1,6 +1,6 @@
 """load_h5ad's filters + normalisation at config-2 size: device path vs the host restatement (same box)."""
 import os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, pandas as pd, torch
 from scipy import sparse
 import bench, scdrs_b200

@@ -3,7 +3,7 @@ symmetric 15-neighbour graph): device path of scdrs_b200.method.downstream_* aga
 (oracle/downstream_oracle.py, vectorised -- the reference itself loops over cells in Python,
 scdrs/method.py:1073-1079) on a bounded sample of the groups.  Writes one JSON object.
 
-    python scratch/bench_downstream.py [--n-cell N] [--n-ctrl C] [--n-group G] [--cpu-groups K]
+    python tests/scripts/bench_downstream.py [--n-cell N] [--n-ctrl C] [--n-group G] [--cpu-groups K]
 """
 import argparse
 import json
@@ -14,8 +14,8 @@ import time
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(HERE, ".."))
-sys.path.insert(0, os.path.join(HERE, "..", "tests"))
 
 import helpers  # noqa: E402
 import scdrs_b200  # noqa: E402
