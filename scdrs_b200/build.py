@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscdrs_b200.so")
-SOURCES = ["api.cu", "spmm_score.cu", "spmm_score_fx.cu", "background.cu", "empi_null.cu", "stats.cu", "counts_pp.cu", "downstream.cu", "ctrl_select.cu", "score_writer.cu"]
+SOURCES = ["api.cu", "spmm_score.cu", "spmm_score_fx.cu", "background.cu", "empi_null.cu", "stats.cu", "counts_pp.cu", "downstream.cu", "ctrl_select.cpp", "score_writer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-pthread", "--expt-relaxed-constexpr",
@@ -48,7 +48,7 @@ def build_native(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

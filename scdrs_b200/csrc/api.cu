@@ -75,8 +75,14 @@ Uploader g_up;
 
 static int h2d_big(scdrs_ctx* c, DevBuf& buf, const void* host, size_t bytes) {
     SCDRS_TRY(buf.reserve(bytes));
-    if (bytes < 4 * kUpChunk) {
+    // a source that is already page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor behind
+    // a numpy view) is copied by the DMA engine directly: one asynchronous copy at link speed, no staging
+    cudaPointerAttributes attr;
+    const bool pinned = bytes > 0 && cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();        // older drivers report unregistered memory as an error: clear it
+    if (pinned || bytes < 4 * kUpChunk) {
         if (bytes) SCDRS_CUDA(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (pinned && bytes >= 4 * kUpChunk) SCDRS_CUDA(cudaStreamSynchronize(c->stream));   // like the staged path
         return 0;
     }
     std::lock_guard<std::mutex> lock(g_up.mu);

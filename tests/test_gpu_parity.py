@@ -800,3 +800,24 @@ def test_pipelined_submit_collect_equals_blocking_call(native_lib):
     with pytest.raises(RuntimeError, match="nothing was submitted"):
         ctx.score_trait_collect(t0)
     scdrs_b200.clear_device_cache()
+
+
+def test_upload_from_pinned_host_memory_round_trips(native_lib):
+    """Large uploads take two routes -- staged through pinned chunks (ordinary numpy arrays) or one direct copy
+    (arrays that already live in page-locked memory): both must put the same bytes on the device."""
+    import torch
+
+    from scdrs_b200 import _native
+
+    rng = np.random.default_rng(0)
+    n_cell, n_gene, per = 9000, 3000, 1000                      # 9e6 entries: 36 MB per array, above the threshold
+    indptr = np.arange(n_cell + 1, dtype=np.int64) * per
+    indices = np.sort(rng.integers(0, n_gene, (n_cell, per)).astype(np.int32), axis=1).reshape(-1)
+    data = rng.random(n_cell * per, dtype=np.float32)
+    pinned = [torch.from_numpy(a).pin_memory() for a in (indptr, indices, data)]
+    for src in ((indptr, indices, data), tuple(t.numpy() for t in pinned)):
+        c = _native.Context(0)
+        c.set_csr_host(src[0], src[1], src[2], n_gene)
+        ip, ix, da = c.get_csr(n_cell * per)
+        assert np.array_equal(ip, indptr) and np.array_equal(ix, indices) and np.array_equal(da, data)
+        c.close()
