@@ -6,7 +6,7 @@ Mirrors the reference's public surface for that path (``scdrs/__init__.py:1-6``)
 ``include/scdrs_b200.h``; there is no CPU fallback.
 """
 from . import method, pp, util  # noqa: F401
-from ._device import clear_device_cache, set_default_device, set_spmm_mode  # noqa: F401
+from ._device import clear_device_cache, invalidate_uploads, set_default_device, set_spmm_mode  # noqa: F401
 from .anndata_lite import AnnData, read_h5ad  # noqa: F401
 from .method import score_cell, score_traits  # noqa: F401
 from .pp import preprocess  # noqa: F401

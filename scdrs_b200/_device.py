@@ -36,6 +36,15 @@ def clear_device_cache():
     _STATES.clear()
 
 
+def invalidate_uploads():
+    """Forget what is resident -- the next call uploads ``adata.X`` and the covariate terms again -- but keep
+    the contexts with their device and pinned buffers (a long-running process scoring one data set after
+    another re-uploads inputs, it does not re-allocate its working memory)."""
+    for st in _STATES.values():
+        st.x_fp = None
+        st.cov_fp = None
+
+
 def _x_fingerprint(X):
     if sparse.issparse(X):
         return ("sp", id(X), id(X.data), X.shape, X.nnz, X.format)

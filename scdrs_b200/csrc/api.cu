@@ -148,6 +148,30 @@ static void release_all(scdrs_ctx* c) {
 
 using namespace scdrs;
 
+// SCDRS_B200_TRACE=1: host time of the stages of a call, to stderr (where does a submit spend its time?)
+#include <chrono>
+namespace {
+struct StageTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    explicit StageTrace(const char* what) : on(false) {
+        const char* e = getenv("SCDRS_B200_TRACE");
+        on = e != nullptr && e[0] == '1';
+        if (on) { t0 = std::chrono::steady_clock::now(); line = what; }
+    }
+    void mark(const char* stage) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " | %s %.2f ms", stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+    ~StageTrace() { if (on) fprintf(stderr, "%s\n", line.c_str()); }
+};
+}  // namespace
+
 #define CTX_GUARD(c)                                                       \
     SCDRS_CHECK((c) != nullptr, "null context");                           \
     SCDRS_CUDA(cudaSetDevice((c)->device))
@@ -493,17 +517,25 @@ int scdrs_score_trait(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctr
     SCDRS_TRY(c->x_col2.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->x_colmin.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->x_hist.reserve((size_t)(c->n_cell + 1) * sizeof(unsigned long long)));
+    StageTrace tr("scdrs_score_trait");
     if (c->timed_trait) SCDRS_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    SCDRS_TRY(scdrs_trait_raw(c, n_ctrl, n_s, n_s_ctrl, trait_genes, trait_gw, ctrl_genes, ctrl_gw,
-                              weight_opt, use_var_ratio, c->x_colsum.as<double>()));
+    SCDRS_TRY(trait_prepare(c, n_ctrl, n_s, n_s_ctrl, trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt,
+                            use_var_ratio));
+    tr.mark("prepare");
+    SCDRS_TRY(spmm_score(c));
+    tr.mark("scatter");
+    SCDRS_TRY(bg_colsum(c, c->x_colsum.as<double>()));
     SCDRS_TRY(scdrs_trait_rowstats(c, c->x_colsum.as<double>(), c->n_cell, c->x_col2.as<double>(),
                                    c->x_colmin.as<double>()));
+    tr.mark("rowstats");
     SCDRS_TRY(scdrs_trait_queries(c, c->x_col2.as<double>(), c->x_colmin.as<double>(), nullptr));
     SCDRS_TRY(trait_count_impl(c, c->query.as<float>(), c->n_cell,
                                c->x_hist.as<unsigned long long>(), ctrl_norm != nullptr));
+    tr.mark("queries+count");
     const int rc = scdrs_trait_finish(c, c->x_hist.as<unsigned long long>(), c->n_cell, 0,
                                       (int64_t)c->n_cell * n_ctrl, raw_score, norm_score, mc_count,
                                       ge_count, ctrl_raw, ctrl_norm);
+    tr.mark("finish");
     if (c->timed_trait) cudaEventRecord(c->ev[3], c->stream);
     return rc;
 }

@@ -384,7 +384,15 @@ def score_traits(
     and returns the list of scored traits when a callback is given.
     """
     import os
+    import time
     from concurrent.futures import ThreadPoolExecutor
+
+    trace = [] if os.environ.get("SCDRS_B200_TRACE", "0") == "1" else None
+    t_start = time.perf_counter()
+
+    def mark(what):
+        if trace is not None:
+            trace.append((what, time.perf_counter() - t_start))
 
     adata = data
     assert "SCDRS_PARAM" in adata.uns, "adata.uns['SCDRS_PARAM'] not found, run `scdrs.pp.preprocess` first"
@@ -425,9 +433,12 @@ def score_traits(
             g, w = dict_gs[t]
             futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
                                   tab, bins, not (share_draws and i_t % world != rank))
+        mark("tables+submit")
         ctx = state.ensure_matrix(adata)
+        mark("matrix resident")
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
+        mark("cov+stats resident")
         if sharded:
             from .distributed import CudaPhases, DrawBroadcaster, ShardedScorer
 
@@ -461,6 +472,7 @@ def score_traits(
             nonlocal in_flight
             for i_t, t in enumerate(traits):
                 prep = futs.pop(t).result()
+                mark("prep %d" % i_t)
                 if share_draws:
                     # the drawn sets travel owner -> pinned -> device -> NCCL broadcast and are consumed on the
                     # device; the other ranks computed everything else about the trait themselves
@@ -479,8 +491,10 @@ def score_traits(
                                                     prep["ctrl_gw"], weight_opt, use_ratio,
                                                     want_ctrl_raw=return_ctrl_raw_score,
                                                     want_ctrl_norm=return_ctrl_norm_score)
+                    mark("submitted %d" % i_t)
                     if in_flight is not None:
                         collect(in_flight)
+                        mark("collected %d" % (i_t - 1))
                     in_flight = (t, ticket)
                     continue
                 out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
@@ -502,6 +516,11 @@ def score_traits(
                     ctx.score_trait_collect(in_flight[1])
                 except Exception:
                     pass
+    mark("done")
+    if trace is not None:
+        import sys
+
+        sys.stderr.write("score_traits trace: " + " | ".join("%s %.3f" % x for x in trace) + "\n")
     np.random.seed(random_seed)
     return results if on_result is None else traits
 
