@@ -605,11 +605,20 @@ def test_score_traits_equal_score_cell(native_lib):
         genes, w = traits[t]
         one = scdrs_b200.score_cell(adata, genes, gene_weight=w, n_ctrl=200, return_ctrl_norm_score=True)
         assert np.array_equal(df.values, one.values, equal_nan=True), t
+    # inputs uploaded again into the buffers the context already owns: same frames
+    scdrs_b200.invalidate_uploads()
+    again = scdrs_b200.score_traits(adata, traits, n_ctrl=200, return_ctrl_norm_score=True)
+    for t, df in seen:
+        assert np.array_equal(df.values, again[t].values, equal_nan=True), t
     # an error inside a worker thread surfaces in the caller
     bad = dict(traits)
     bad["broken"] = (["not_a_gene"], [1.0])
     with pytest.raises(Exception):
         scdrs_b200.score_traits(adata, bad, n_ctrl=20)
+    # ... and leaves the context usable (the trait in flight was collected and dropped)
+    ok = scdrs_b200.score_traits(adata, {k: traits[k] for k in list(traits)[:2]}, n_ctrl=200, return_ctrl_norm_score=True)
+    for t in ok:
+        assert np.array_equal(ok[t].values, again[t].values, equal_nan=True), t
 
 
 def test_categorical_custom_match_key(sc):
