@@ -60,8 +60,8 @@ def _upload_scores(ctx, df, cols, rows=None):
 
 def _quantile_positions(sizes, q):
     """numpy's index arithmetic for np.quantile(x, q) (method "linear") on a sample of each size: the lower
-    order statistic and the interpolation weight (numpy/lib/_function_base_impl.py: _compute_virtual_index
-    with alpha = beta = 1, _get_indexes, _get_gamma)."""
+    order statistic and the interpolation weight (numpy/lib/_function_base_impl.py: virtual index
+    (n - 1) * q of the "linear" method, _get_indexes, _get_gamma)."""
     sizes = np.asarray(sizes, dtype=np.int64)
     quantiles = np.float64(q)
     lo = np.zeros(sizes.shape[0], np.int32)
@@ -69,7 +69,7 @@ def _quantile_positions(sizes, q):
     for i, n in enumerate(sizes):
         if n <= 0:
             continue
-        virtual = int(n) * quantiles + (1.0 + quantiles * (1 - 1.0 - 1.0)) - 1
+        virtual = (int(n) - 1) * quantiles
         prev = np.floor(virtual)
         if virtual >= n - 1:
             lo[i], gamma[i] = n - 1, 0.0

@@ -275,3 +275,71 @@ def test_munge_gs_cli_known_answers(tmp_path):
     assert df.loc["HEIGHT", "GENESET"] == "OR4F5:1,BPY2B:1"
     with pytest.raises(AssertionError, match="One of --pval-file"):
         cli.main(["munge-gs", "--out-file", out])
+
+
+# ---- host side of the downstream analyses (scdrs_b200/downstream.py) ------------------------------
+def test_quantile_positions_reproduce_numpy():
+    """The (lower index, weight) handed to the device must be numpy's own for every group size."""
+    from scdrs_b200 import downstream as ds
+
+    rng = np.random.default_rng(0)
+    sizes = np.arange(1, 260)
+    for q in (0.95, 0.5, 0.0, 1.0, 0.013):
+        lo, gamma = ds._quantile_positions(sizes, q)
+        for n, a, t in zip(sizes, lo, gamma):
+            x = np.sort(rng.normal(size=n))
+            hi = min(a + 1, n - 1)
+            d = x[hi] - x[a]
+            got = x[hi] - d * (1 - t) if t >= 0.5 else x[a] + d * t
+            assert got == np.quantile(x, q), (n, q)
+
+
+def test_group_layout_and_graph_equal_scipy_slicing():
+    """order / grp_ptr and the within-group sub-graph against ``graph[idx][:, idx]`` per group."""
+    from scipy import sparse
+
+    from scdrs_b200 import downstream as ds
+
+    rng = np.random.default_rng(1)
+    n, n_group = 300, 7
+    codes = rng.integers(0, n_group, n)
+    codes[codes == 3] = 2                                    # an empty group
+    G = sparse.random(n, n, density=0.05, random_state=2, format="csr", dtype=np.float32)
+    order, grp_ptr = ds._group_layout(codes, n_group)
+    indptr, nbr, w = ds._group_graph(G, codes, order)
+    w_sum = ds._group_weight_sums((indptr, nbr, w), grp_ptr)
+    for g in range(n_group):
+        idx = np.nonzero(codes == g)[0]
+        assert np.array_equal(order[grp_ptr[g]:grp_ptr[g + 1]], idx)
+        want = G[idx][:, idx].toarray().astype(np.float64)
+        a, b = grp_ptr[g], grp_ptr[g + 1]
+        got = np.zeros((b - a, b - a))
+        for p in range(a, b):
+            for e in range(indptr[p], indptr[p + 1]):
+                assert a <= nbr[e] < b
+                got[p - a, nbr[e] - a] = w[e]
+        assert np.array_equal(got, want)
+        assert np.isclose(w_sum[g], want.sum())
+
+
+def test_align_equals_sorted_intersection():
+    from scdrs_b200 import downstream as ds
+    from scdrs_b200.anndata_lite import AnnData
+    from scipy import sparse
+
+    names = ["c%03d" % i for i in np.random.default_rng(3).permutation(50)]
+    adata = AnnData(sparse.csr_matrix((50, 2), dtype=np.float32), pd.DataFrame(index=names))
+    df = pd.DataFrame({"norm_score": np.arange(40.0)}, index=names[5:35][::-1] + ["x%d" % i for i in range(10)])
+    df_rows, rows = ds._align(adata, df)
+    cell_list = sorted(set(adata.obs_names) & set(df.index))
+    assert list(df.index[df_rows]) == cell_list and list(adata.obs_names[rows]) == cell_list
+
+
+def test_load_scdrs_score_reads_the_toy_folder():
+    d = util.load_scdrs_score(os.path.join(helpers.TOY, "@.full_score.gz"))
+    assert list(d) == ["toydata_gs_mouse.ref_Ctrl20_CovConstCovariate"]
+    df = d["toydata_gs_mouse.ref_Ctrl20_CovConstCovariate"]
+    assert df.shape == (30, 26) and "ctrl_norm_score_19" in df.columns
+    assert util.load_scdrs_score(os.path.join(helpers.TOY, "@.full_score.gz"), obs_names=["nobody"] * 100) == {}
+    with pytest.raises(AssertionError, match="full_score.gz"):
+        util.load_scdrs_score(os.path.join(helpers.TOY, "@.score.gz"))
