@@ -31,8 +31,7 @@ def _align(adata, df_full_score):
     in_adata = adata.obs_names.get_indexer(df_full_score.index)
     if df_full_score.index.is_unique and adata.obs_names.is_unique:
         df_rows = np.nonzero(in_adata >= 0)[0]
-        names = np.asarray(df_full_score.index.values[df_rows], dtype=object)
-        by_name = np.argsort(names, kind="stable")
+        by_name = np.asarray(df_full_score.index[df_rows].argsort())       # unique names: any sort is stable
         return df_rows[by_name], in_adata[df_rows][by_name]
     cell_list = sorted(set(adata.obs_names) & set(df_full_score.index))
     return df_full_score.index.get_indexer(cell_list), adata.obs_names.get_indexer(cell_list)
@@ -91,21 +90,20 @@ def _group_layout(codes, n_group):
 
 def _group_graph(graph, codes, order):
     """The neighbour graph with cells in group order, edges between groups dropped: what
-    ``adata[group_index].obsp["connectivities"]`` holds for every group at once.  Returns
-    (indptr, nbr, w) and the sum of the weights inside every group."""
+    ``adata[group_index].obsp["connectivities"]`` holds for every group at once.  Returns the CSR parts
+    (indptr int64, neighbour positions int32, weights float64); the entries of a row keep their stored order."""
     G = sparse.csr_matrix(graph)
     assert G.shape[0] == G.shape[1]
     n = G.shape[0]
     codes = np.asarray(codes, dtype=np.int64)
-    coo = G.tocoo()
-    keep = codes[coo.row] == codes[coo.col]
+    Gp = G[order]                                            # rows in group order (a C-level row gather)
+    row_p = np.repeat(np.arange(n, dtype=np.int64), np.diff(Gp.indptr))
+    keep = codes[order][row_p] == codes[Gp.indices]
     pos = np.empty(n, np.int64)
     pos[order] = np.arange(n, dtype=np.int64)
-    row, col = pos[coo.row[keep]], pos[coo.col[keep]]
-    w = coo.data[keep].astype(np.float64, copy=False)
-    sub = sparse.csr_matrix((w, (row, col)), shape=(n, n))
-    sub.sort_indices()
-    return sub.indptr.astype(np.int64), sub.indices.astype(np.int32), sub.data.astype(np.float64)
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(row_p[keep], minlength=n), out=indptr[1:])
+    return indptr, pos[Gp.indices[keep]].astype(np.int32), Gp.data[keep].astype(np.float64)
 
 
 def _geary_from_totals(total, denom, n_in_group, w_in_group):
@@ -242,7 +240,7 @@ def downstream_group_analysis(adata, df_full_score, group_cols, fdr_thresholds=[
 
     dict_df_res = {}
     for group_col in group_cols:
-        group_list = sorted(set(adata.obs[group_col]))
+        group_list = sorted(pd.unique(adata.obs[group_col]))              # = sorted(set(...)), :771
         res_cols = ["n_cell", "n_ctrl", "assoc_mcp", "assoc_mcz", "hetero_mcp", "hetero_mcz"]
         for fdr_threshold in fdr_thresholds:
             res_cols.append(f"n_fdr_{fdr_threshold}")
