@@ -197,23 +197,18 @@ def test_gearysc(adata, df_full_score, groupby, opt="control_distribution_match"
         _upload_scores(ctx, df_full_score, ["norm_score"] + ctrl_cols)
     _, C = _gearys_by_group(ctx, codes, len(groups), adata.obsp["connectivities"], mode)
 
-    df_stats = pd.DataFrame(index=index_groups, columns=["trait"] + [f"null_{i}" for i in range(n_null)], data=np.nan)
-    df_stats.loc[groups, :] = C
-    trait_col = "trait"
-    null_cols = [col for col in df_stats.columns if col.startswith("null_")]
-    pval = ((df_stats[trait_col].values > df_stats[null_cols].values.T).sum(axis=0) + 1) / (len(null_cols) + 1)
-    pval[np.isnan(df_stats[trait_col])] = np.nan
-    df_rls = pd.DataFrame(
-        {
-            "pval": pval,
-            "trait": df_stats[trait_col].values,
-            "ctrl_mean": df_stats[null_cols].mean(axis=1).values,
-            "ctrl_std": df_stats[null_cols].std(axis=1).values,
-        },
-        index=df_stats.index,
-    )
-    df_rls["zsc"] = -(df_rls[trait_col].values - df_rls["ctrl_mean"]) / df_rls["ctrl_std"]
-    return df_rls
+    # per group: Geary's C of the trait against its controls                     scdrs/method.py:1022-1040
+    trait, null = C[:, 0], C[:, 1:]
+    pval = ((trait[:, None] > null).sum(axis=1) + 1) / (n_null + 1)
+    pval[np.isnan(trait)] = np.nan
+    with np.errstate(divide="ignore", invalid="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)                # groups without edges: all NaN
+        ctrl_mean = np.nanmean(null, axis=1)
+        ctrl_std = np.nanstd(null, axis=1, ddof=1) if n_null > 1 else np.full(len(groups), np.nan)
+        zsc = -(trait - ctrl_mean) / ctrl_std
+    df_rls = pd.DataFrame({"pval": pval, "trait": trait, "ctrl_mean": ctrl_mean, "ctrl_std": ctrl_std, "zsc": zsc},
+                          index=groups)
+    return df_rls.reindex(index_groups)             # rows in order of first appearance, like the reference
 
 
 test_gearysc.__test__ = False     # a library function named like the reference's, not a pytest test

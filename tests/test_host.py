@@ -343,3 +343,34 @@ def test_load_scdrs_score_reads_the_toy_folder():
     assert util.load_scdrs_score(os.path.join(helpers.TOY, "@.full_score.gz"), obs_names=["nobody"] * 100) == {}
     with pytest.raises(AssertionError, match="full_score.gz"):
         util.load_scdrs_score(os.path.join(helpers.TOY, "@.score.gz"))
+
+
+def test_downstream_host_logic_against_committed_reference_outputs(monkeypatch):
+    """The host side of the downstream analyses (everything but the three device calls, which a numpy stand-in
+    answers here) reproduces what the unmodified reference returned for tests/golden/ref_downstream_case.npz and
+    the reference's golden files for the toy data."""
+    from fake_device import NumpyDownstreamContext
+
+    from scdrs_b200 import downstream as ds
+
+    fake = NumpyDownstreamContext()
+    monkeypatch.setattr(ds, "_ctx", lambda: fake)
+    adata, df, ref = helpers.load_downstream_case()
+    grp = ds.downstream_group_analysis(adata, df, ["grp"])["grp"]
+    assert list(grp.columns) == list(ref["group"].columns) and all(dt == np.float32 for dt in grp.dtypes)
+    np.testing.assert_allclose(grp.loc[ref["group"].index].values.astype(float), ref["group"].values, rtol=1e-5, equal_nan=True)
+    corr = ds.downstream_corr_analysis(adata, df, ["v1", "v2"])
+    np.testing.assert_allclose(corr.values.astype(float), ref["corr"], rtol=1e-5)
+    order = sorted(adata.obs_names)
+    sub, dfo = adata[order], df.loc[order]
+    for opt, key in (("control_distribution_match", "rls"), ("control", "rls_ctrl")):
+        rls = ds.test_gearysc(sub, dfo, "grp", opt=opt)
+        assert list(rls.index) == list(ref[key].index) and list(rls.columns) == list(ref[key].columns)
+        np.testing.assert_allclose(rls.values, ref[key].values, rtol=1e-9, equal_nan=True)
+    assert abs(ds.gearys_c(adata, df["norm_score"].values) - ref["gearys_c"]) < 1e-12
+
+    toy, _, _, toy_ref, _ = helpers.load_toy()
+    full = toy_ref["REF_COV_FULL"]
+    gold = pd.read_csv(os.path.join(helpers.TOY, "toydata_gs_mouse.ref_Ctrl20_CovConstCovariate.scdrs_cell_corr"), sep="\t", index_col=0)
+    got = ds.downstream_corr_analysis(toy, full, list(gold.index))
+    np.testing.assert_allclose(got.values, gold.values, rtol=2e-6)
