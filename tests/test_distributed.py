@@ -80,6 +80,16 @@ class NumpyPhases:
                     ctrl_norm=self.c32 if want_ctrl_norm else None)
 
 
+    # the two halves of `finish` (the CUDA phases keep results in pinned slots; here they are simply held)
+    def finish_submit(self, hist, n_query_all, offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm):
+        self._held = self.finish(hist, n_query_all, offset, n_null_total, n_ctrl, want_ctrl_raw, want_ctrl_norm)
+        return (0, n_ctrl, want_ctrl_raw, want_ctrl_norm)
+
+    def collect(self, ticket):
+        out, self._held = self._held, None
+        return out
+
+
 def _make_problem():
     from oracle import scdrs_oracle as orc
     from scdrs_b200 import synth
@@ -111,6 +121,13 @@ def _run_rank(rank, world, port, out_dir):
         assert scorer.n_total == n and scorer.offset == lo
         # control weights: every control position inherits the trait weight of its bin position
         out = scorer.score(idx, tgw, info["ctrl_cols"], _ctrl_gw(info), "vs", True, want_ctrl_norm=True)
+        # the pipelined entry points run the same phases and collectives
+        ticket = scorer.submit(idx, tgw, info["ctrl_cols"], _ctrl_gw(info), "vs", True, want_ctrl_norm=True)
+        again = scorer.collect(ticket)
+        assert again["n_null_total"] == out["n_null_total"]
+        for k, v in out.items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(v, again[k], equal_nan=True), k
         np.savez(os.path.join(out_dir, "rank%d_of%d.npz" % (rank, world)), lo=lo, hi=hi,
                  **{k: v for k, v in out.items() if isinstance(v, np.ndarray)})
     finally:
