@@ -864,6 +864,7 @@ int scdrs_ds_group_stats(scdrs_ctx* c, int32_t n_group, const int64_t* order, co
     CTX_GUARD(c);
     SCDRS_CHECK(c->ds_n > 0, "no score matrix set (scdrs_ds_set_scores)");
     SCDRS_CHECK(n_group > 0 && order != nullptr && grp_ptr != nullptr, "null pointer");
+    SCDRS_CHECK(n_group <= 65535, "at most 65535 cell groups per call (got %d)", n_group);
     SCDRS_CHECK(geary_mode >= 0 && geary_mode <= 2, "geary_mode must be 0, 1 or 2");
     SCDRS_CHECK(quantile == nullptr || (q_lo != nullptr && q_gamma != nullptr), "quantile positions missing");
     SCDRS_CHECK(geary_mode == 0 || (g_indptr && geary_total && geary_denom), "graph or outputs missing");
