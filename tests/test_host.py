@@ -53,6 +53,23 @@ def test_select_ctrl_draws_equal_numpy_legacy_generator(native_lib, seed):
     assert np.array_equal(got, np.array(want))
 
 
+def test_select_ctrl_full_permutations_at_mask_boundaries(native_lib):
+    """Bin sizes around every power of two (where the rejection mask of the index draw changes), whole
+    permutations (k = n), many draws per bin so that generator refills fall inside a shuffle."""
+    sizes = np.array([1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 1024, 1025])
+    bin_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    bin_genes = np.arange(bin_ptr[-1], dtype=np.int32)
+    ntrait = sizes.astype(np.int32)
+    n_ctrl, n_s = 9, int(ntrait.sum())
+    got = _native.select_ctrl(2024, bin_ptr, bin_genes, ntrait, n_ctrl, n_s)
+    rs = np.random.RandomState(2024)
+    want = np.empty((n_ctrl, n_s), np.int64)
+    for b, n in enumerate(sizes):
+        for i in range(n_ctrl):
+            want[i, bin_ptr[b]:bin_ptr[b + 1]] = bin_ptr[b] + rs.permutation(int(n))
+    assert np.array_equal(got, want)
+
+
 def test_select_ctrl_equals_np_random_choice_on_strings(native_lib):
     names = sorted("g%03d" % i for i in range(57))
     np.random.seed(7)
