@@ -391,3 +391,24 @@ def test_downstream_host_logic_against_committed_reference_outputs(monkeypatch):
     gold = pd.read_csv(os.path.join(helpers.TOY, "toydata_gs_mouse.ref_Ctrl20_CovConstCovariate.scdrs_cell_corr"), sep="\t", index_col=0)
     got = ds.downstream_corr_analysis(toy, full, list(gold.index))
     np.testing.assert_allclose(got.values, gold.values, rtol=2e-6)
+
+
+def test_downstream_group_labels_categorical_or_integer(monkeypatch):
+    """Real AnnData annotations are usually categorical (with unused categories) or integers."""
+    from fake_device import NumpyDownstreamContext
+
+    from scdrs_b200 import downstream as ds
+
+    fake = NumpyDownstreamContext()
+    monkeypatch.setattr(ds, "_ctx", lambda: fake)
+    adata, df, ref = helpers.load_downstream_case()
+    want = ds.downstream_group_analysis(adata, df, ["grp"])["grp"]
+    adata.obs["grp_cat"] = pd.Categorical(adata.obs["grp"], categories=["g4", "g3", "g2", "g1", "g0", "unused"])
+    adata.obs["grp_int"] = np.asarray([int(g[1:]) for g in adata.obs["grp"]])
+    res = ds.downstream_group_analysis(adata, df, ["grp_cat", "grp_int"])
+    assert list(res["grp_cat"].index) == list(want.index) and list(res["grp_int"].index) == [0, 1, 2, 3, 4]
+    for key in ("grp_cat", "grp_int"):
+        np.testing.assert_allclose(res[key].values.astype(float), want.values.astype(float), equal_nan=True)
+    order = sorted(adata.obs_names)
+    rls = ds.test_gearysc(adata[order], df.loc[order], "grp_cat")
+    np.testing.assert_allclose(rls.loc[ref["rls"].index].values, ref["rls"].values, rtol=1e-9, equal_nan=True)
