@@ -412,3 +412,35 @@ def test_downstream_group_labels_categorical_or_integer(monkeypatch):
     order = sorted(adata.obs_names)
     rls = ds.test_gearysc(adata[order], df.loc[order], "grp_cat")
     np.testing.assert_allclose(rls.loc[ref["rls"].index].values, ref["rls"].values, rtol=1e-9, equal_nan=True)
+
+
+def test_downstream_score_frame_layouts(monkeypatch):
+    """The three ways a score frame reaches the device (whole frame + column picks, a column sub-frame when
+    dtypes are mixed, gathered rows when the frame holds cells the AnnData does not) give the same statistics."""
+    from fake_device import NumpyDownstreamContext
+
+    from scdrs_b200 import downstream as ds
+
+    fake = NumpyDownstreamContext()
+    monkeypatch.setattr(ds, "_ctx", lambda: fake)
+    adata, df, _ = helpers.load_downstream_case()
+    want = ds.downstream_group_analysis(adata, df, ["grp"])["grp"].values.astype(float)
+    want_corr = ds.downstream_corr_analysis(adata, df, ["v1", "v2"]).values.astype(float)
+
+    mixed = df.copy()
+    mixed["norm_score"] = mixed["norm_score"].astype(np.float32).astype(np.float64)      # same values ...
+    mixed["pval"] = mixed["pval"].astype(np.float32)                                      # ... mixed dtypes
+    mixed["norm_score"] = df["norm_score"]
+    extra = pd.DataFrame(np.random.default_rng(0).normal(size=(7, df.shape[1])), columns=df.columns,
+                         index=["stranger%d" % i for i in range(7)])
+    bigger = pd.concat([df.iloc[:100], extra, df.iloc[100:]])
+    fortran = pd.DataFrame(np.asfortranarray(df.values), index=df.index, columns=df.columns)
+    for frame in (mixed, bigger, fortran):
+        got = ds.downstream_group_analysis(adata, frame, ["grp"])["grp"].values.astype(float)
+        tol = dict(rtol=1e-6) if frame is mixed else dict(rtol=1e-12)
+        if frame is mixed:       # float32 p-values can move an FDR count at a threshold; compare the rest
+            np.testing.assert_allclose(got[:, :6], want[:, :6], equal_nan=True, **tol)
+        else:
+            np.testing.assert_allclose(got, want, equal_nan=True, **tol)
+        np.testing.assert_allclose(ds.downstream_corr_analysis(adata, frame, ["v1", "v2"]).values.astype(float),
+                                   want_corr, rtol=1e-9)
