@@ -218,6 +218,12 @@ int scdrs_ds_group_stats(scdrs_ctx* ctx, int32_t n_group, const int64_t* order, 
  * ctrl_genes[n_ctrl x n_s]; bit-identical to np.random.seed(seed) + np.random.choice(...). */
 int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr, const int32_t* bin_genes,
                       const int32_t* bin_ntrait, int32_t n_ctrl, int32_t n_s, int32_t* ctrl_genes);
+/* Same, and mt_state_out[625] (may be NULL) receives the generator after the draws -- numpy's key[624] and pos --
+ * so that the caller can leave numpy's GLOBAL generator where the reference leaves it (the reference draws on
+ * it, scdrs/method.py:96, 276, 301: callers observe that side effect). */
+int scdrs_select_ctrl_state(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr, const int32_t* bin_genes,
+                            const int32_t* bin_ntrait, int32_t n_ctrl, int32_t n_s, int32_t* ctrl_genes,
+                            uint32_t* mt_state_out);
 
 /* ---- host code: score-file writer (bin/scdrs:276-288; format docs/file_format.rst:81-108) --------
  * Gzip TSV: `header` (one line, '\n'-terminated), then per row: name, then n_col float32 fields in

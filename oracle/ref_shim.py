@@ -5,17 +5,28 @@ The two hot-path source files, /root/reference/scdrs/pp.py and /root/reference/s
 nevertheless execute unmodified once those third-party modules are stubbed in ``sys.modules``.
 This file does exactly that and nothing else; no reference code is copied.
 
-It only works where ``/root/reference`` exists (the build container).  It is used by
-``tests/golden/make_golden.py`` to produce the committed fixtures and by the container-only
-tests that compare ``oracle/scdrs_oracle.py`` with the live reference.  The GPU box has no
-``/root/reference``: nothing on the ``-m gpu`` / smoke / bench path imports this module.
+The sources are looked for under ``$SCDRS_REFERENCE_ROOT``, ``/root/reference`` (the build container) and
+``oracle/_ref`` (the git-ignored copy ``oracle/stage_ref.py`` stages so that it travels to the GPU box).  It is
+used by ``tests/golden/make_golden.py`` to produce the committed fixtures, by the container-only tests that
+compare ``oracle/scdrs_oracle.py`` with the live reference, and by ``bench.py``'s CPU legs (``cpu_baseline`` /
+``--impl reference``), which time the reference's own ``score_cell`` where the staged copy exists and fall back to
+the numpy port otherwise.  Nothing under ``scdrs_b200/`` imports this module.
 """
 import importlib.util
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("SCDRS_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("SCDRS_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")):
+        if cand and os.path.exists(os.path.join(cand, "scdrs", "method.py")) and \
+                os.path.exists(os.path.join(cand, "scdrs", "pp.py")):
+            return cand
+    return os.environ.get("SCDRS_REFERENCE_ROOT", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available():

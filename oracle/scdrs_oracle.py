@@ -117,22 +117,28 @@ def compute_raw_score(X, pos, w, cov_mat=None, cov_beta=None, gene_mean=None):
 # ----------------------------------------------------------------------------------------------
 # background correction                                                 scdrs/method.py:482-598
 # ----------------------------------------------------------------------------------------------
-def correct_background(v_raw, mat_ctrl, var_ratio):
-    """Restates scdrs/method.py:521-583 (the optional text dumps are not part of the path)."""
+def correct_background(v_raw, mat_ctrl, var_ratio, inject=None):
+    """Restates scdrs/method.py:521-583 (the optional text dumps are not part of the path).
+
+    ``inject`` (tests of a SLICE of a larger atlas only): the statistics the reference takes over all cells --
+    ``raw_mean`` [1 + n_ctrl] (:526-527), ``norm_mean`` [1 + n_ctrl] (:564-565), ``lo`` (:581) -- supplied from
+    the full run, column 0 being the trait; everything cell-wise is computed here as the reference does."""
     v_raw = np.asarray(v_raw, dtype=np.float64)
     mat_ctrl = np.asarray(mat_ctrl, dtype=np.float64)
     zero_t = v_raw == 0                                   # :522
     zero_c = mat_ctrl == 0                                # :523
-    t = v_raw - v_raw.mean()                              # :526
-    c = (mat_ctrl - mat_ctrl.mean(axis=0)) / np.sqrt(var_ratio)   # :527-528
+    raw_mean_t = v_raw.mean() if inject is None else inject["raw_mean"][0]
+    raw_mean_c = mat_ctrl.mean(axis=0) if inject is None else inject["raw_mean"][1:]
+    t = v_raw - raw_mean_t                                # :526
+    c = (mat_ctrl - raw_mean_c) / np.sqrt(var_ratio)      # :527-528
     mu = c.mean(axis=1)                                   # :544
     sd = c.std(axis=1)                                    # :545
     with np.errstate(divide="ignore", invalid="ignore"):
         t = (t - mu) / sd                                 # :547
         c = ((c.T - mu) / sd).T                           # :548
-    t = t - t.mean()                                      # :564
-    c = c - c.mean(axis=0)                                # :565
-    lo = min(t.min(), c.min())                            # :581
+    t = t - (t.mean() if inject is None else inject["norm_mean"][0])          # :564
+    c = c - (c.mean(axis=0) if inject is None else inject["norm_mean"][1:])   # :565
+    lo = min(t.min(), c.min()) if inject is None else inject["lo"]            # :581
     t[zero_t] = lo - 1e-3                                 # :582
     c[zero_c] = lo                                        # :583
     return t, c
@@ -168,8 +174,10 @@ def score_cell(
     return_ctrl_norm_score=False,
     random_seed=0,
     return_internals=False,
+    inject=None,
 ):
-    """Restates scdrs/method.py:96-226 on top of the helpers above."""
+    """Restates scdrs/method.py:96-226 on top of the helpers above.  ``inject``: see ``correct_background`` (the
+    pooled p-value is then taken against the slice's own null and is only meaningful to the caller as such)."""
     param = adata.uns["SCDRS_PARAM"]
     n_cell, n_gene = adata.shape
     df_gene = param["GENE_STATS"].loc[adata.var_names].copy()      # :146
@@ -221,7 +229,7 @@ def score_cell(
             ratio[i] = (var[ctrl_pos[i]] * mat_w[:, i] ** 2).sum()
         ratio /= (var[trait_pos] * v_w ** 2).sum()
 
-    v_norm, mat_norm = correct_background(v_raw, mat_raw, ratio)    # :197
+    v_norm, mat_norm = correct_background(v_raw, mat_raw, ratio, inject)    # :197
     mc_count = (mat_norm.T >= v_norm).sum(axis=0)                   # :205
     mc_p = (1 + mc_count) / (1 + n_ctrl)
     null = mat_norm.flatten()

@@ -3,6 +3,7 @@
 every call, scdrs/method.py:98-99, :389-400)."""
 import os
 import weakref
+import zlib
 
 import numpy as np
 from scipy import sparse
@@ -30,7 +31,7 @@ def set_spmm_mode(mode):
 
 
 def clear_device_cache():
-    """Drop every resident matrix (call after mutating ``adata.X`` in place)."""
+    """Drop every resident matrix and context (frees the device memory)."""
     for st in list(_STATES.values()):
         st.close()
     _STATES.clear()
@@ -45,10 +46,32 @@ def invalidate_uploads():
         st.cov_fp = None
 
 
+_N_STAMP = 1 << 16
+
+
+def _sample_crc(a):
+    """CRC of up to 65,536 evenly spaced elements of a flat array plus its two ends (about 0.3 ms)."""
+    a = np.asarray(a).reshape(-1)
+    n = a.shape[0]
+    if n == 0:
+        return 0
+    if os.environ.get("SCDRS_B200_STRICT_STAMP", "0") == "1":
+        return zlib.crc32(np.ascontiguousarray(a).view(np.uint8))
+    step = max(1, n // _N_STAMP)
+    crc = zlib.crc32(np.ascontiguousarray(a[::step]).view(np.uint8))
+    return zlib.crc32(np.ascontiguousarray(a[-min(n, 64):]).view(np.uint8), crc)
+
+
 def _x_fingerprint(X):
+    """Content stamp of ``adata.X``: shape, stored entries and a CRC of sampled values / column ids / row pointers.
+    It does not depend on object identity, so an in-place edit (``X.data *= 2``, ``np.log1p(X.data, out=X.data)``)
+    changes it -- the resident copy is then replaced instead of silently scoring the old matrix -- while anndata
+    views that hand out a new ``.X`` object per access keep the resident copy.  ``SCDRS_B200_STRICT_STAMP=1``
+    checksums every byte."""
     if sparse.issparse(X):
-        return ("sp", id(X), id(X.data), X.shape, X.nnz, X.format)
-    return ("dn", id(X), X.shape, str(X.dtype))
+        return ("sp", X.shape, int(X.nnz), X.format, str(X.dtype), _sample_crc(X.data), _sample_crc(X.indices),
+                _sample_crc(X.indptr))
+    return ("dn", X.shape, str(X.dtype), _sample_crc(X))
 
 
 def to_csr_parts(X):

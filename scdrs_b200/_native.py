@@ -75,6 +75,8 @@ SIGNATURES = {
                                        C.c_void_p]),
     "scdrs_select_ctrl": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_void_p]),
+    "scdrs_select_ctrl_state": (C.c_int, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
     "scdrs_write_score_gz": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_int32]),
     "scdrs_format_f32": (C.c_int, [C.c_float, C.c_char_p]),
@@ -417,13 +419,17 @@ class Context:
         return quant, total, denom
 
 
-def select_ctrl(seed, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s):
-    """Host-only: numpy-legacy-RNG control gene draws (see include/scdrs_b200.h)."""
+def select_ctrl(seed, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s, want_state=False):
+    """Host-only: numpy-legacy-RNG control gene draws (see include/scdrs_b200.h).  With ``want_state`` also the
+    generator after the draws, as the tuple ``np.random.set_state`` takes."""
     bin_ptr, bin_genes = as_c(bin_ptr, np.int32), as_c(bin_genes, np.int32)
     bin_ntrait = as_c(bin_ntrait, np.int32)
     out = np.empty((n_ctrl, n_s), np.int32)
-    check(lib().scdrs_select_ctrl(int(seed) & 0xFFFFFFFF, bin_ntrait.shape[0], ptr(bin_ptr), ptr(bin_genes),
-                                  ptr(bin_ntrait), int(n_ctrl), int(n_s), ptr(out)))
+    state = np.empty(625, np.uint32) if want_state else None
+    check(lib().scdrs_select_ctrl_state(int(seed) & 0xFFFFFFFF, bin_ntrait.shape[0], ptr(bin_ptr), ptr(bin_genes),
+                                        ptr(bin_ntrait), int(n_ctrl), int(n_s), ptr(out), ptr(state)))
+    if want_state:
+        return out, ("MT19937", state[:624].copy(), int(state[624]), 0, 0.0)
     return out
 
 

@@ -93,9 +93,9 @@ inline void shuffle_from_top(MT19937& rng, int32_t* __restrict__ perm, int32_t n
 
 }  // namespace
 
-extern "C" int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr,
-                                 const int32_t* bin_genes, const int32_t* bin_ntrait, int32_t n_ctrl,
-                                 int32_t n_s, int32_t* ctrl_genes) {
+extern "C" int scdrs_select_ctrl_state(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr,
+                                       const int32_t* bin_genes, const int32_t* bin_ntrait, int32_t n_ctrl,
+                                       int32_t n_s, int32_t* ctrl_genes, uint32_t* mt_state_out) {
     SCDRS_CHECK(n_bin >= 0 && n_ctrl >= 0 && n_s >= 0, "negative size");
     SCDRS_CHECK(bin_ptr && bin_genes && bin_ntrait && (ctrl_genes || n_ctrl == 0), "null pointer");
     MT19937 rng(seed);
@@ -120,5 +120,15 @@ extern "C" int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bi
         off += k;
     }
     SCDRS_CHECK(off == n_s, "trait genes per bin sum to %lld, expected n_s = %d", (long long)off, n_s);
+    if (mt_state_out != nullptr) {      // numpy's legacy state after the same draws: key[624], then pos
+        memcpy(mt_state_out, rng.mt, 624 * sizeof(uint32_t));
+        mt_state_out[624] = (uint32_t)rng.pos;
+    }
     return 0;
+}
+
+extern "C" int scdrs_select_ctrl(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr,
+                                 const int32_t* bin_genes, const int32_t* bin_ntrait, int32_t n_ctrl,
+                                 int32_t n_s, int32_t* ctrl_genes) {
+    return scdrs_select_ctrl_state(seed, n_bin, bin_ptr, bin_genes, bin_ntrait, n_ctrl, n_s, ctrl_genes, nullptr);
 }

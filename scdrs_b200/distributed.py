@@ -69,22 +69,51 @@ class CudaPhases:
 class ShardedScorer:
     """Scores one trait over cells sharded across the ranks of the default process group."""
 
-    def __init__(self, phases, device):
+    def __init__(self, phases, device, group=None):
+        """group: the ranks that share one atlas (None: the default group; False: this process alone, whatever
+        torch.distributed says -- trait-sharded runs, where every rank holds all cells)."""
         self.p = phases
         self.device = device
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.group = None if group is False else group
+        alone = group is False or not dist.is_initialized()
+        self.world = 1 if alone else dist.get_world_size(self.group)
+        self.rank = 0 if alone else dist.get_rank(self.group)
         n_local = int(phases.n_cell)
         if self.world > 1:
             sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
             sizes[self.rank] = n_local
-            dist.all_reduce(sizes)
+            dist.all_reduce(sizes, group=self.group)
             self.sizes = [int(s) for s in sizes.tolist()]
         else:
             self.sizes = [n_local]
         self.n_total = sum(self.sizes)
         self.offset = sum(self.sizes[: self.rank])
         self._buf = {}
+        self.timing = None        # dict -> per-phase CUDA-event times are collected (bench.py)
+        self._marks = []
+
+    # ---- optional per-phase timing: CUDA events on the compute stream around phases and collectives ----
+    def _mark(self, name):
+        if self.timing is None or self.device.type != "cuda":
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._marks.append((name, ev))
+
+    def _close_marks(self):
+        if self.timing is None or len(self._marks) < 2:
+            self._marks = []
+            return
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(self._marks[:-1], self._marks[1:]):
+            self.timing.setdefault(name, []).append(e0.elapsed_time(e1))
+        self._marks = []
+
+    def timing_summary(self):
+        """{phase_ms: mean over the timed traits} (None when nothing was timed)."""
+        if not self.timing:
+            return None
+        return {k + "_ms": float(np.mean(v)) for k, v in self.timing.items()}
 
     def _tensor(self, name, n, dtype):
         t = self._buf.get(name)
@@ -98,14 +127,14 @@ class ShardedScorer:
             return q_local
         q_all = self._tensor("q_all", self.n_total, torch.float32)
         if len(set(self.sizes)) == 1:
-            dist.all_gather_into_tensor(q_all, q_local)
+            dist.all_gather_into_tensor(q_all, q_local, group=self.group)
         else:
             # ragged shards: gather blocks padded to the largest shard, then compact
             m = max(self.sizes)
             pad = self._tensor("q_pad", m, torch.float32)
             pad[: q_local.shape[0]].copy_(q_local)
             blocks = self._tensor("q_blocks", m * self.world, torch.float32)
-            dist.all_gather_into_tensor(blocks, pad)
+            dist.all_gather_into_tensor(blocks, pad, group=self.group)
             off = 0
             for r, n in enumerate(self.sizes):
                 q_all[off: off + n].copy_(blocks[r * m: r * m + n])
@@ -127,8 +156,11 @@ class ShardedScorer:
         """``score`` without waiting for the GPU: everything (collectives included) is queued on the stream and
         the results land in pinned memory; ``collect(ticket)`` returns them.  At most two tickets outstanding."""
         hist, n_ctrl = self._phases_1_to_4(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio)
-        return self.p.finish_submit(hist, self.n_total, self.offset, self.n_total * n_ctrl, n_ctrl,
-                                    want_ctrl_raw, want_ctrl_norm)
+        ticket = self.p.finish_submit(hist, self.n_total, self.offset, self.n_total * n_ctrl, n_ctrl,
+                                      want_ctrl_raw, want_ctrl_norm)
+        self._mark("finish")
+        self._close_marks()
+        return ticket
 
     def collect(self, ticket):
         out = self.p.collect(ticket)
@@ -146,18 +178,28 @@ class ShardedScorer:
         q_local = self._tensor("q_local", self.sizes[self.rank], torch.float32)
         hist = self._tensor("hist", self.n_total + 1, torch.int64)
 
+        self._mark("start")
         self.p.raw(trait_genes, trait_gw, ctrl_genes, ctrl_gw, weight_opt, use_ratio, colsum)
+        self._mark("raw")
         if self.world > 1:
-            dist.all_reduce(colsum)
+            dist.all_reduce(colsum, group=self.group)
+            self._mark("colsum_allreduce")
         self.p.rowstats(colsum, self.n_total, col2, colmin)
+        self._mark("rowstats")
         if self.world > 1:
-            dist.all_reduce(col2)
-            dist.all_reduce(colmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(col2, group=self.group)
+            dist.all_reduce(colmin, op=dist.ReduceOp.MIN, group=self.group)
+            self._mark("col2_min_allreduce")
         self.p.queries(col2, colmin, q_local)
+        self._mark("queries")
         q_all = self._gather_queries(q_local)
-        self.p.count(q_all, hist)
         if self.world > 1:
-            dist.all_reduce(hist)
+            self._mark("query_allgather")
+        self.p.count(q_all, hist)
+        self._mark("count")
+        if self.world > 1:
+            dist.all_reduce(hist, group=self.group)
+            self._mark("hist_allreduce")
         return hist, n_ctrl
 
 
@@ -166,8 +208,9 @@ class DrawBroadcaster:
     drew them into a device buffer on every rank, without a host round trip on the receivers: pinned staging on
     the owner, NCCL broadcast on the stream the kernels run on.  Two buffers alternate (two traits in flight)."""
 
-    def __init__(self, device, cap):
+    def __init__(self, device, cap, group=None):
         self.device = device
+        self.group = group
         self.dev = [torch.empty(cap, dtype=torch.int32, device=device) for _ in range(2)]
         self.pin = [torch.empty(cap, dtype=torch.int32, pin_memory=(device.type == "cuda")) for _ in range(2)]
         self.k = 0
@@ -181,36 +224,5 @@ class DrawBroadcaster:
         if ctrl_cols is not None:
             self.pin[k][:m].copy_(torch.from_numpy(np.ascontiguousarray(ctrl_cols, dtype=np.int32).reshape(-1)))
             buf.copy_(self.pin[k][:m], non_blocking=True)
-        dist.broadcast(buf, src=src)
+        dist.broadcast(buf, src=src if self.group is None else dist.get_global_rank(self.group, src), group=self.group)
         return buf.view(n_ctrl, n_sc)
-
-
-def broadcast_prep(prep, src, n_ctrl, n_s_max, device):
-    """Ship one trait's host-drawn gene sets (``method._prepare_trait``) from rank ``src`` to all ranks.
-
-    One int32 buffer over NCCL: [n_s, n_sc, trait_cols, ctrl_cols, trait_gw (f64 bits), ctrl_gw (f64 bits)],
-    sized for the largest possible trait (n_s_max genes) so that receivers need no size exchange."""
-    cap = 2 + n_s_max + n_ctrl * n_s_max + 4 * n_s_max
-    if prep is not None:
-        n_s, n_sc = int(prep["trait_cols"].shape[0]), int(prep["ctrl_cols"].shape[1])
-        host = np.empty(cap, dtype=np.int32)
-        host[0], host[1] = n_s, n_sc
-        o = 2
-        host[o:o + n_s] = prep["trait_cols"]; o += n_s
-        host[o:o + n_ctrl * n_sc] = np.ascontiguousarray(prep["ctrl_cols"], dtype=np.int32).reshape(-1); o += n_ctrl * n_sc
-        host[o:o + 2 * n_s] = np.ascontiguousarray(prep["trait_gw"], dtype=np.float64).view(np.int32); o += 2 * n_s
-        host[o:o + 2 * n_sc] = np.ascontiguousarray(prep["ctrl_gw"], dtype=np.float64).view(np.int32)
-        buf = torch.from_numpy(host).to(device)
-    else:
-        buf = torch.empty(cap, dtype=torch.int32, device=device)
-    dist.broadcast(buf, src=src)
-    if prep is not None:
-        return prep
-    host = buf.cpu().numpy()
-    n_s, n_sc = int(host[0]), int(host[1])
-    o = 2
-    trait_cols = host[o:o + n_s].copy(); o += n_s
-    ctrl_cols = host[o:o + n_ctrl * n_sc].reshape(n_ctrl, n_sc).copy(); o += n_ctrl * n_sc
-    trait_gw = host[o:o + 2 * n_s].copy().view(np.float64); o += 2 * n_s
-    ctrl_gw = host[o:o + 2 * n_sc].copy().view(np.float64)
-    return dict(trait_cols=trait_cols, trait_gw=trait_gw, ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw)

@@ -74,14 +74,16 @@ def _ctrl_layout(bins, trait_pos, trait_gw):
 
 
 def _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=None):
-    """Control sets as integer positions; see include/scdrs_b200.h:scdrs_select_ctrl.
+    """Control sets as integer positions; see include/scdrs_b200.h:scdrs_select_ctrl_state.
 
-    trait_pos must be ordered by gene name.  Returns (ctrl_pos[n_ctrl, n_sc], ctrl_gw[n_sc]).
+    trait_pos must be ordered by gene name.  Returns (ctrl_pos[n_ctrl, n_sc], ctrl_gw[n_sc], rng_state):
+    rng_state is numpy's legacy generator after the draws (what the reference leaves behind in ``np.random``).
     """
     ntrait, ctrl_gw = _ctrl_layout(bins, trait_pos, trait_gw)
     genes = bins.bin_pos if col_of is None else col_of[bins.bin_pos]
-    ctrl = _native.select_ctrl(random_seed, bins.bin_ptr, genes, ntrait, n_ctrl, int(ntrait.sum()))
-    return ctrl, ctrl_gw
+    ctrl, rng_state = _native.select_ctrl(random_seed, bins.bin_ptr, genes, ntrait, n_ctrl, int(ntrait.sum()),
+                                          want_state=True)
+    return ctrl, ctrl_gw, rng_state
 
 
 # ----------------------------------------------------------------------------------------------
@@ -105,9 +107,10 @@ def score_cell(
     ``raw_score, norm_score, mc_pval, pval, nlog10_pval, zscore[, ctrl_raw_score_*][, ctrl_norm_score_*]``).
 
     Differences from the reference, all outside the numerical contract: ``adata.X`` is NOT
-    converted to CSC in place (:98-99); the global numpy generator is re-seeded (:96) but not
-    advanced by the control draws; ``weight_opt="od"`` (benchmarking only, :352-355) and
-    ``save_intermediate`` text dumps are not part of the accelerated path and raise.
+    converted to CSC in place (:98-99); ``weight_opt="od"`` (benchmarking only, :352-355) and
+    ``save_intermediate`` text dumps are not part of the accelerated path and raise.  The global
+    numpy generator is left exactly where the reference leaves it (re-seeded, :96 / :276, then
+    advanced by the control draws, :301).
     """
     np.random.seed(random_seed)                                       # :96
     adata = data.copy() if copy else data
@@ -152,6 +155,7 @@ def score_cell(
     implicit = bool(param["FLAG_SPARSE"] and param["FLAG_COV"])
     state = get_state(adata)
     prep = _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl, n_genebin, random_seed)
+    np.random.set_state(prep["rng_state"])                            # the draws of :301 were made on np.random
     if verbose:
         print("# scdrs.method.score_cell: use %d overlapping genes for scoring" % len(prep["genes"]))
 
@@ -222,11 +226,11 @@ def _prepare_trait(adata, state, gene_list, gene_weight, ctrl_match_key, n_ctrl,
     if bins is None:
         bins = _bins_for(tab.df_gene, ctrl_match_key, n_genebin, state.bins_cache if state is not None else None)
     if draw:
-        ctrl_cols, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=tab.col_of)
+        ctrl_cols, ctrl_gw, rng_state = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed, col_of=tab.col_of)
     else:
-        ctrl_cols, ctrl_gw = None, _ctrl_layout(bins, trait_pos, trait_gw)[1]
+        ctrl_cols, ctrl_gw, rng_state = None, _ctrl_layout(bins, trait_pos, trait_gw)[1], None
     return dict(genes=genes, trait_cols=tab.col_of[trait_pos].astype(np.int32), trait_gw=trait_gw,
-                ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=tab.var, var_tech=tab.var_tech)
+                ctrl_cols=ctrl_cols, ctrl_gw=ctrl_gw, var=tab.var, var_tech=tab.var_tech, rng_state=rng_state)
 
 
 def _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score):
@@ -277,7 +281,8 @@ def _select_ctrl_geneset(input_df_gene, gene_list, gene_weight, ctrl_match_key, 
     trait_pos = pos_index.get_indexer(genes).astype(np.int64)
     trait_gw = np.array([dic_gene_weight[x] for x in genes], dtype=np.float64)
     bins = _GeneBins(df_gene, ctrl_match_key, n_genebin)
-    ctrl_pos, ctrl_gw = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed)
+    ctrl_pos, ctrl_gw, rng_state = _draw_ctrl(bins, trait_pos, trait_gw, n_ctrl, random_seed)
+    np.random.set_state(rng_state)                                        # :301 draws on the global generator
     # weights come back as the caller's own objects, like the reference's lists
     w_list = [dic_gene_weight[genes[i]] for i in
               np.flatnonzero(bins.code[trait_pos] >= 0)[np.argsort(bins.code[trait_pos][bins.code[trait_pos] >= 0], kind="stable")]]
@@ -355,6 +360,59 @@ def _scratch_context():
 # ----------------------------------------------------------------------------------------------
 # many traits against one data set (what `scdrs compute-score` loops over, bin/scdrs:255-274)
 # ----------------------------------------------------------------------------------------------
+def _shard_layout(sharded, shard):
+    """(mode, world, rank, n_trait_group, trait_group, cell_group) of this process.
+
+    mode "single": one process, one GPU.  "cells": the ranks of `cell_group` hold the cell shards of one atlas.
+    "traits": every rank holds all cells and scores traits[rank::world].  A grid (t, c) combines both: rank =
+    trait_group * c + cell_shard; the c ranks of a trait group hold the c cell shards and score
+    traits[trait_group::t]."""
+    if shard is None:
+        shard = "cells" if sharded else None
+    if shard is None:
+        return "single", 1, 0, 1, 0, None
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return "single", 1, 0, 1, 0, None
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if shard == "cells":
+        return "cells", world, rank, 1, 0, None
+    if shard == "traits":
+        return "traits", world, rank, world, rank, None
+    n_tg, n_cs = (int(x) for x in shard)
+    assert n_tg * n_cs == world, "shard grid %d x %d does not match the %d ranks" % (n_tg, n_cs, world)
+    if n_cs == 1:
+        return "traits", world, rank, world, rank, None
+    if n_tg == 1:
+        return "cells", world, rank, 1, 0, None
+    mine = None
+    for tg in range(n_tg):              # every rank creates every group, in the same order
+        grp = dist.new_group(ranks=list(range(tg * n_cs, (tg + 1) * n_cs)))
+        if tg == rank // n_cs:
+            mine = grp
+    return "cells", world, rank, n_tg, rank // n_cs, mine
+
+
+def _check_ranks_agree(adata, tab, ctrl_match_key, group, device):
+    """Cell-sharded scoring needs the SAME gene-level parameters on every rank (same bins -> same control sets,
+    same weights); a rank that preprocessed its own shard alone would silently score against different sets."""
+    import torch
+    import torch.distributed as dist
+
+    gs = tab.df_gene
+    h = int(pd.util.hash_pandas_object(gs[["var", "var_tech", ctrl_match_key]], index=True).values.sum()) & ((1 << 62) - 1)
+    param = adata.uns["SCDRS_PARAM"]
+    if "COV_BETA" in param:
+        h ^= int(pd.util.hash_pandas_object(param["COV_BETA"], index=True).values.sum()) & ((1 << 62) - 1)
+    t = torch.tensor([h, -h], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    if int(t[0].item()) != -int(t[1].item()):
+        raise RuntimeError(
+            "score_traits(sharded): GENE_STATS / COV_BETA differ between ranks -- run preprocess(..., sharded=True) "
+            "(statistics over the cells of all ranks) or give every rank the same SCDRS_PARAM gene tables")
+
+
 def score_traits(
     data,
     dict_gs,
@@ -369,19 +427,28 @@ def score_traits(
     n_jobs=None,
     on_result=None,
     sharded=False,
+    shard=None,
+    max_prefetch=None,
 ):
     """Score every gene set of ``dict_gs`` = {trait: (gene_list, gene_weight_list)}.
 
-    ``sharded=True`` (one process per GPU under torchrun, ``torch.distributed`` initialised):
-    ``data`` holds this rank's block of cells; the gene-set alignment statistics and the pooled
-    empirical null span the cells of all ranks (``scdrs_b200.distributed.ShardedScorer``), every
-    rank draws the same control sets, and the returned frames cover this rank's cells.
+    One process per GPU under torchrun (``torch.distributed`` initialised), three ways to split the work:
+
+    * ``shard="cells"`` (= ``sharded=True``): ``data`` holds this rank's block of cells; the gene-set alignment
+      statistics and the pooled empirical null span the cells of all ranks
+      (``scdrs_b200.distributed.ShardedScorer``), the control-set draws are dealt over the ranks and broadcast, and
+      the returned frames cover this rank's cells.  The gene-level parameters must be those of the whole atlas
+      (``preprocess(..., sharded=True)``); this is checked.
+    * ``shard="traits"``: every rank holds ALL cells and scores ``traits[rank::world]`` -- the reference's own
+      parallelism (``.gs`` batches over array jobs, bin/scdrs:255-274), no collective at all.
+    * ``shard=(t, c)``: a grid of t trait groups x c cell shards (rank = trait_group * c + cell_shard).
 
     Each trait gets exactly what ``score_cell`` would return for it (every call re-seeds, so traits
     are independent, scdrs/method.py:96, :276); the host work of upcoming traits (gene
-    intersection and the control-gene draws, which release the GIL) runs in worker threads while
-    the GPU scores the current one.  Returns {trait: DataFrame}, or feeds ``on_result(trait, df)``
-    and returns the list of scored traits when a callback is given.
+    intersection and the control-gene draws, which release the GIL) runs in worker threads, at most
+    ``max_prefetch`` traits ahead, while the GPU scores the current one; result frames are built and handed to
+    ``on_result(trait, df)`` (in ``.gs`` order) off the critical path.  Returns {trait: DataFrame}, or the list of
+    scored traits when a callback is given.
     """
     import os
     import time
@@ -408,53 +475,66 @@ def score_traits(
     implicit = bool(param["FLAG_SPARSE"] and param["FLAG_COV"])
     state = get_state(adata)
     use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))
-    traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
-    if not traits:
+    mode, world, rank, n_tg, my_tg, cell_group = _shard_layout(sharded, shard)
+    all_traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
+    traits = all_traits[my_tg::n_tg] if n_tg > 1 else all_traits
+    if not traits and mode != "cells":
         return {} if on_result is None else []
     # per-dataset tables once, outside the pool
     tab = _gene_table(adata, state)
     bins = _GeneBins(tab.df_gene, ctrl_match_key, n_genebin)
-    n_jobs = n_jobs or max(1, min(len(traits), (os.cpu_count() or 2) - 1, 16))
+    n_jobs = n_jobs or max(1, min(len(traits) or 1, (os.cpu_count() or 2) - 1, 16))
+    window = max(2, max_prefetch if max_prefetch is not None else 2 * n_jobs)
     results = {}
-    with ThreadPoolExecutor(max_workers=n_jobs) as pool, ThreadPoolExecutor(max_workers=2) as frame_pool:
-        # the control draws of every trait start now; the upload of X overlaps with the first of them
-        world, rank = 1, 0
-        if sharded:
+    last_rng_state = [None]
+    cell_sharded = mode == "cells"
+    with ThreadPoolExecutor(max_workers=n_jobs) as pool, ThreadPoolExecutor(max_workers=2) as frame_pool, \
+            ThreadPoolExecutor(max_workers=1) as writer:
+        if cell_sharded:
             import torch
             import torch.distributed as dist
 
-            if dist.is_initialized():
-                world, rank = dist.get_world_size(), dist.get_rank()
-        # Every rank needs the same control sets; the draws (~0.2 s of one core per trait) are dealt
-        # round-robin over the ranks and broadcast, instead of every rank drawing all of them.
-        share_draws = world > 1 and os.environ.get("SCDRS_B200_LOCAL_DRAWS", "0") != "1"
+            g_world, g_rank = dist.get_world_size(cell_group), dist.get_rank(cell_group)
+        else:
+            g_world, g_rank = 1, 0
+        # Every rank of a cell group needs the same control sets; the draws (~0.1 s of one core per trait) are
+        # dealt round-robin over the group's ranks and broadcast, instead of every rank drawing all of them.
+        share_draws = g_world > 1 and os.environ.get("SCDRS_B200_LOCAL_DRAWS", "0") != "1"
         futs = {}
-        for i_t, t in enumerate(traits):
-            g, w = dict_gs[t]
-            futs[t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin, random_seed,
-                                  tab, bins, not (share_draws and i_t % world != rank))
+        n_submitted = [0]
+
+        def prefetch(upto):
+            # host work (intersection + control draws) of the traits [n_submitted, upto): a bounded window, so a
+            # .gs file with thousands of sets does not pile up drawn control matrices (4 MB each at the defaults)
+            while n_submitted[0] < min(upto, len(traits)):
+                i_t = n_submitted[0]
+                g, w = dict_gs[traits[i_t]]
+                futs[i_t] = pool.submit(_prepare_trait, adata, state, g, w, ctrl_match_key, n_ctrl, n_genebin,
+                                        random_seed, tab, bins, not (share_draws and i_t % g_world != g_rank))
+                n_submitted[0] += 1
+
+        prefetch(window)          # the draws start now; the upload of X overlaps with the first of them
         mark("tables+submit")
         ctx = state.ensure_matrix(adata)
         mark("matrix resident")
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
         mark("cov+stats resident")
-        if sharded:
+        if cell_sharded:
             from .distributed import CudaPhases, DrawBroadcaster, ShardedScorer
 
             dev = torch.device("cuda", torch.cuda.current_device())
-            scorer = ShardedScorer(CudaPhases(ctx, dev), dev)
-            score_one = scorer.score
-            if share_draws:
-                shipper = DrawBroadcaster(dev, n_ctrl * max(len(dict_gs[t][0]) for t in traits))
-        else:
-            score_one = ctx.score_trait
+            _check_ranks_agree(adata, tab, ctrl_match_key, cell_group, dev)
+            scorer = ShardedScorer(CudaPhases(ctx, dev), dev, group=cell_group)
+            if share_draws and traits:
+                shipper = DrawBroadcaster(dev, n_ctrl * max(len(dict_gs[t][0]) for t in traits), group=cell_group)
         pending = []          # (trait, future of the result frame): frames are built off the critical path
-        in_flight = None      # (trait, ticket) submitted to the GPU and not collected yet (single GPU)
+        written = []          # futures of on_result calls (one writer thread: .gs order is kept)
+        in_flight = None      # (trait, ticket) submitted to the GPU and not collected yet
 
         def collect(item):
             t_prev, ticket = item
-            out_prev = scorer.collect(ticket) if sharded else ctx.score_trait_collect(ticket)
+            out_prev = scorer.collect(ticket) if cell_sharded else ctx.score_trait_collect(ticket)
             pending.append((t_prev, frame_pool.submit(_result_frame, adata, out_prev, n_ctrl, return_ctrl_raw_score,
                                                       return_ctrl_norm_score)))
             drain(2)
@@ -466,47 +546,44 @@ def score_traits(
                 if on_result is None:
                     results[t_done] = df_done
                 else:
-                    on_result(t_done, df_done)
+                    written.append(writer.submit(on_result, t_done, df_done))
+                    while len(written) > 4:          # back-pressure: frames are large (n_cell x 1006 by default)
+                        written.pop(0).result()
 
         def run_all():
             nonlocal in_flight
             for i_t, t in enumerate(traits):
-                prep = futs.pop(t).result()
+                prefetch(i_t + 1 + window)
+                prep = futs.pop(i_t).result()
+                if prep["rng_state"] is not None:
+                    last_rng_state[0] = prep["rng_state"]
                 mark("prep %d" % i_t)
-                if share_draws:
-                    # the drawn sets travel owner -> pinned -> device -> NCCL broadcast and are consumed on the
+                if cell_sharded:
+                    # shared draws travel owner -> pinned -> device -> NCCL broadcast and are consumed on the
                     # device; the other ranks computed everything else about the trait themselves
-                    d_ctrl = shipper.ship(prep["ctrl_cols"], i_t % world, n_ctrl, prep["ctrl_gw"].shape[0])
-                    ticket = scorer.submit(prep["trait_cols"], prep["trait_gw"], d_ctrl, prep["ctrl_gw"], weight_opt,
+                    ctrl = shipper.ship(prep["ctrl_cols"], i_t % g_world, n_ctrl, prep["ctrl_gw"].shape[0]) \
+                        if share_draws else prep["ctrl_cols"]
+                    ticket = scorer.submit(prep["trait_cols"], prep["trait_gw"], ctrl, prep["ctrl_gw"], weight_opt,
                                            use_ratio, want_ctrl_raw=return_ctrl_raw_score,
                                            want_ctrl_norm=return_ctrl_norm_score)
-                    if in_flight is not None:
-                        collect(in_flight)
-                    in_flight = (t, ticket)
-                    continue
-                if not sharded:
+                else:
                     # the next trait is queued behind the current one before the current one's results are
                     # fetched: the GPU never waits for the host between traits
                     ticket = ctx.score_trait_submit(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"],
                                                     prep["ctrl_gw"], weight_opt, use_ratio,
                                                     want_ctrl_raw=return_ctrl_raw_score,
                                                     want_ctrl_norm=return_ctrl_norm_score)
-                    mark("submitted %d" % i_t)
-                    if in_flight is not None:
-                        collect(in_flight)
-                        mark("collected %d" % (i_t - 1))
-                    in_flight = (t, ticket)
-                    continue
-                out = score_one(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"],
-                                weight_opt, use_ratio, want_ctrl_raw=return_ctrl_raw_score,
-                                want_ctrl_norm=return_ctrl_norm_score)
-                pending.append((t, frame_pool.submit(_result_frame, adata, out, n_ctrl, return_ctrl_raw_score,
-                                                     return_ctrl_norm_score)))
-                drain(2)
+                mark("submitted %d" % i_t)
+                if in_flight is not None:
+                    collect(in_flight)
+                    mark("collected %d" % (i_t - 1))
+                in_flight = (t, ticket)
             if in_flight is not None:
                 last, in_flight = in_flight, None
                 collect(last)
             drain(0)
+            for w_ in written:
+                w_.result()
 
         try:
             run_all()
@@ -521,7 +598,10 @@ def score_traits(
         import sys
 
         sys.stderr.write("score_traits trace: " + " | ".join("%s %.3f" % x for x in trace) + "\n")
+    # numpy's global generator: where the reference's loop over traits would leave it (after the last trait's draws)
     np.random.seed(random_seed)
+    if last_rng_state[0] is not None:
+        np.random.set_state(last_rng_state[0])
     return results if on_result is None else traits
 
 

@@ -78,6 +78,57 @@ def test_select_ctrl_equals_np_random_choice_on_strings(native_lib):
     assert [[names[j] for j in row] for row in got] == want
 
 
+def test_select_ctrl_leaves_numpy_global_generator_where_the_reference_does(native_lib):
+    """The reference draws on numpy's GLOBAL generator (scdrs/method.py:96, 276, 301): whatever a caller draws from
+    np.random after score_cell / _select_ctrl_geneset must be the same numbers as after the reference."""
+    names = sorted("g%03d" % i for i in range(300))
+    df_gene = pd.DataFrame(index=names, data={"mean": np.linspace(0, 1, 300)})
+    genes = names[::7]
+    np.random.seed(11)                                     # what the reference does: seed, then choice() per bin x set
+    bins = pd.qcut(df_gene["mean"], q=10, labels=False, duplicates="drop")
+    for b in sorted(set(bins)):
+        members = sorted(set(df_gene.index[bins == b]))
+        hit = sorted(set(members) & set(genes))
+        for _ in range(6):
+            np.random.choice(members, size=len(hit), replace=False)
+    want_next = np.random.random(5)
+    np.random.seed(999)                                    # some other state: the call must re-seed like the reference
+    method._select_ctrl_geneset(df_gene, genes, [1.0] * len(genes), "mean", 6, 10, 11)
+    assert np.array_equal(np.random.random(5), want_next)
+    # and the state tuple itself against a RandomState walked through the same draws
+    got, state = _native.select_ctrl(5, [0, 40, 100], np.arange(100), [3, 4], 8, 7, want_state=True)
+    rs = np.random.RandomState(5)
+    for n, k in ((40, 3), (60, 4)):
+        for _ in range(8):
+            rs.permutation(n)
+    ref_state = rs.get_state()
+    assert np.array_equal(state[1], ref_state[1]) and state[2] == ref_state[2]
+
+
+def test_resident_matrix_stamp_detects_in_place_edits():
+    """adata.X edited in place (X.data *= 2, np.log1p(out=...)) must not be scored from the stale resident copy:
+    the residency key is a content stamp, not object identity (and a new-but-equal .X object keeps the copy)."""
+    from scipy import sparse as sp_
+
+    from scdrs_b200 import _device
+
+    rng = np.random.default_rng(0)
+    X = sp_.random(500, 300, density=0.1, format="csr", random_state=1, dtype=np.float32)
+    fp0 = _device._x_fingerprint(X)
+    assert _device._x_fingerprint(X.copy()) == fp0                    # new object, same content: still resident
+    X.data *= 2
+    fp1 = _device._x_fingerprint(X)
+    assert fp1 != fp0
+    np.log1p(X.data, out=X.data)
+    assert _device._x_fingerprint(X) not in (fp0, fp1)
+    X.indices[-1] = (X.indices[-1] + 1) % 300
+    assert _device._x_fingerprint(X) != fp1
+    D = rng.random((50, 40))
+    fd = _device._x_fingerprint(D)
+    D[7, 3] += 1.0
+    assert _device._x_fingerprint(D) != fd
+
+
 def test_select_ctrl_rejects_bad_input(native_lib):
     with pytest.raises(RuntimeError, match="trait genes"):
         _native.select_ctrl(0, [0, 3], [0, 1, 2], [5], 2, 5)
