@@ -183,6 +183,30 @@ int scdrs_gene_cell_stats(scdrs_ctx* ctx, int32_t transform, const double* cell_
  * with scipy's float32 operation order; xtc[n_gene x k] f64 = (C^T X)^T accumulated in cell order. */
 int scdrs_gene_mean_xtc(scdrs_ctx* ctx, int32_t k, const double* cov_mat, float* gene_mean, double* xtc);
 
+/* The same reductions in parallel form: per-gene moments of THIS context's cells in one pass over the stored
+ * entries, no dense block, bitwise reproducible (fixed-order sums, no atomics).  They are plain sums over cells,
+ * so the moments of the shards of several GPUs add up (all-reduce) to those of the whole atlas -- the distributed
+ * form of scdrs/pp.py:206-212 and :353-373.  cell_weight[n_cell] or NULL (weights 1); host pointers.
+ *   mode 0: out[n_gene x (2 + k)] = sum w x, sum w x^2, sum w x cov_mat[c, j] (j < k; cov_mat[n_cell x k], k >= 0)
+ *           -> gene means, C^T X of the regression, and -- with the k x k covariate moments, host algebra, see
+ *           scdrs_b200/pp.py -- mean / var of X + COV_MAT*COV_BETA + COV_GENE_MEAN (_get_mean_var_implicit_cov_corr)
+ *   mode 1: out[n_gene x 2] = sum w expm1(x), sum w expm1(x)^2   (normal mode, scdrs/pp.py:358-364) */
+int scdrs_gene_moments(scdrs_ctx* ctx, int32_t mode, int32_t k, const double* cov_mat, const double* cell_weight,
+                       double* out);
+/* Implicit mode, expm1 scale (scdrs/pp.py:371-373): with v = X + COV_MAT*COV_BETA + COV_GENE_MEAN of the resident
+ * covariate terms (scdrs_set_cov) and a per-gene shift K[n_gene] near the mean,
+ *   out[n_gene x 2] = sum_c w (expm1(v) - K), sum_c w (expm1(v) - K)^2   over ALL cells of this context
+ * (a dense pass over cells x genes plus what the stored entries change). */
+int scdrs_gene_expm1_implicit(scdrs_ctx* ctx, const double* shift, const double* cell_weight, double* out);
+/* scdrs_gene_cell_stats' per-gene sums, strictly in numpy's operation order, for the listed tiles of
+ * scdrs_gene_tile_size() consecutive genes only (genes whose variance is rounding noise of that order).
+ * mean_in[n_gene] != NULL with center == 1: only the centred pass, around the given means (sharded atlases).
+ * gene_sum / gene_sumsq [n_gene]: entries outside the listed tiles are left untouched. */
+int scdrs_gene_stats_exact(scdrs_ctx* ctx, int32_t transform, const double* cell_weight, int32_t center, double denom,
+                           int32_t n_tile, const int32_t* tile_ids, const double* mean_in, double* gene_sum,
+                           double* gene_sumsq);
+int scdrs_gene_tile_size(void);
+
 /* ---- downstream analyses of one trait's score matrix -------------
  * scdrs.method.downstream_corr_analysis / downstream_group_analysis / test_gearysc / gearys_c
  * (scdrs/method.py:712-865, 915-1085).  The caller uploads the trait's scores once, straight from the

@@ -67,6 +67,11 @@ SIGNATURES = {
     "scdrs_gene_cell_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scdrs_gene_mean_xtc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_moments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_expm1_implicit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_stats_exact": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scdrs_gene_tile_size": (C.c_int, []),
     "scdrs_ds_set_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                       C.c_int64, C.c_void_p]),
     "scdrs_ds_corr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -373,6 +378,42 @@ class Context:
         check(self._L.scdrs_gene_cell_stats(self._h, int(transform), ptr(w), int(bool(center)), float(denom),
                                             ptr(gs), ptr(gq), ptr(cs), ptr(cq)))
         return gs, gq, cs, cq
+
+    def gene_moments(self, mode, cov_mat=None, cell_weight=None):
+        """Per-gene moments of this context's cells (scdrs_gene_moments): mode 0 -> [n_gene x (2 + k)] =
+        sum w x, sum w x^2, sum w x C[:, j]; mode 1 -> [n_gene x 2] = sum w expm1(x), sum w expm1(x)^2."""
+        k = 0
+        if mode == 0 and cov_mat is not None:
+            cov_mat = as_c(cov_mat, np.float64)
+            assert cov_mat.shape[0] == self.n_cell
+            k = cov_mat.shape[1]
+        w = None if cell_weight is None else as_c(cell_weight, np.float64)
+        out = np.empty((self.n_gene, 2 + k if mode == 0 else 2), np.float64)
+        check(self._L.scdrs_gene_moments(self._h, int(mode), int(k), ptr(cov_mat) if k else None, ptr(w), ptr(out)))
+        return out
+
+    def gene_expm1_implicit(self, shift, cell_weight=None):
+        """[n_gene x 2] = sum_c w (expm1(v) - shift), sum_c w (expm1(v) - shift)^2 over all cells (implicit mode)."""
+        shift = as_c(shift, np.float64)
+        assert shift.shape[0] == self.n_gene
+        w = None if cell_weight is None else as_c(cell_weight, np.float64)
+        out = np.empty((self.n_gene, 2), np.float64)
+        check(self._L.scdrs_gene_expm1_implicit(self._h, ptr(shift), ptr(w), ptr(out)))
+        return out
+
+    def gene_stats_exact(self, transform, genes, gene_sum, gene_sumsq, cell_weight=None, center=False, denom=0.0,
+                         mean_in=None):
+        """Overwrite gene_sum / gene_sumsq (float64 [n_gene], in place) for the tiles that hold `genes` with the
+        sequential, numpy-ordered sums of scdrs_gene_cell_stats.  Returns the gene indices that were recomputed."""
+        ts = int(self._L.scdrs_gene_tile_size())
+        tiles = np.unique(np.asarray(genes, dtype=np.int64) // ts).astype(np.int32)
+        w = None if cell_weight is None else as_c(cell_weight, np.float64)
+        m = None if mean_in is None else as_c(mean_in, np.float64)
+        assert gene_sum.dtype == np.float64 and gene_sumsq.dtype == np.float64
+        check(self._L.scdrs_gene_stats_exact(self._h, int(transform), ptr(w), int(bool(center)), float(denom),
+                                             tiles.shape[0], ptr(tiles), ptr(m), ptr(gene_sum), ptr(gene_sumsq)))
+        idx = (tiles[:, None].astype(np.int64) * ts + np.arange(ts)[None, :]).reshape(-1)
+        return idx[idx < self.n_gene]
 
     # ---- downstream analyses of one trait's score matrix (include/scdrs_b200.h) ----
     def ds_set_scores(self, frame, cols=None):

@@ -816,6 +816,82 @@ int scdrs_gene_mean_xtc(scdrs_ctx* c, int32_t k, const double* cov_mat, float* g
     return rc;
 }
 
+int scdrs_gene_moments(scdrs_ctx* c, int32_t mode, int32_t k, const double* cov_mat, const double* cell_weight,
+                       double* out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    SCDRS_CHECK(out != nullptr && (mode != 0 || k == 0 || cov_mat != nullptr), "null pointer");
+    const int64_t n = c->n_cell;
+    const int g = c->n_gene;
+    const int n_acc = mode == 0 ? 2 + k : 2;
+    DevBuf d_cov, d_w;
+    int rc = 0;
+    if (mode == 0 && k > 0) rc = h2d(c, d_cov, cov_mat, (size_t)n * k * sizeof(double));
+    if (rc == 0 && cell_weight) rc = h2d(c, d_w, cell_weight, (size_t)n * sizeof(double));
+    if (rc == 0) rc = c->stage.reserve((size_t)g * n_acc * sizeof(double));
+    if (rc == 0) rc = gene_moments(c, mode, k, d_cov.as<double>(), cell_weight ? d_w.as<double>() : nullptr, c->stage.as<double>());
+    if (rc == 0) rc = d2h(c, out, c->stage.p, (size_t)g * n_acc * sizeof(double));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    d_cov.release();
+    d_w.release();
+    return rc;
+}
+
+int scdrs_gene_expm1_implicit(scdrs_ctx* c, const double* shift, const double* cell_weight, double* out) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    SCDRS_CHECK(shift != nullptr && out != nullptr, "null pointer");
+    const int64_t n = c->n_cell;
+    const int g = c->n_gene;
+    DevBuf d_shift, d_w;
+    int rc = h2d(c, d_shift, shift, (size_t)g * sizeof(double));
+    if (rc == 0 && cell_weight) rc = h2d(c, d_w, cell_weight, (size_t)n * sizeof(double));
+    if (rc == 0) rc = c->stage.reserve((size_t)g * 2 * sizeof(double));
+    if (rc == 0) rc = gene_expm1_implicit(c, d_shift.as<double>(), cell_weight ? d_w.as<double>() : nullptr, c->stage.as<double>());
+    if (rc == 0) rc = d2h(c, out, c->stage.p, (size_t)g * 2 * sizeof(double));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    d_shift.release();
+    d_w.release();
+    return rc;
+}
+
+int scdrs_gene_tile_size(void) { return gene_tile_size(); }
+
+int scdrs_gene_stats_exact(scdrs_ctx* c, int32_t transform, const double* cell_weight, int32_t center, double denom,
+                           int32_t n_tile, const int32_t* tile_ids, const double* mean_in, double* gene_sum,
+                           double* gene_sumsq) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set");
+    SCDRS_CHECK(n_tile >= 1 && tile_ids && gene_sum && gene_sumsq, "null pointer");
+    const int64_t n = c->n_cell;
+    const int g = c->n_gene, ts = gene_tile_size();
+    for (int i = 0; i < n_tile; ++i)
+        SCDRS_CHECK(tile_ids[i] >= 0 && (int64_t)tile_ids[i] * ts < g, "gene tile %d out of range", tile_ids[i]);
+    DevBuf d_w, d_tiles, d_mean;
+    int rc = h2d(c, d_tiles, tile_ids, (size_t)n_tile * sizeof(int32_t));
+    if (rc == 0 && cell_weight) rc = h2d(c, d_w, cell_weight, (size_t)n * sizeof(double));
+    if (rc == 0 && mean_in) rc = h2d(c, d_mean, mean_in, (size_t)g * sizeof(double));
+    if (rc == 0) rc = c->stage.reserve((size_t)2 * g * sizeof(double));
+    double* d_gs = c->stage.as<double>();
+    double* d_gq = d_gs + g;
+    if (rc == 0)
+        rc = gene_stats_exact(c, transform, cell_weight ? d_w.as<double>() : nullptr, center, denom, n_tile,
+                              d_tiles.as<int32_t>(), mean_in ? d_mean.as<double>() : nullptr, d_gs, d_gq);
+    std::vector<double> hs((size_t)g), hq((size_t)g);
+    if (rc == 0) rc = d2h(c, hs.data(), d_gs, (size_t)g * 8) || d2h(c, hq.data(), d_gq, (size_t)g * 8);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == 0) { set_error("stream sync failed"); rc = 1; }
+    if (rc == 0)
+        for (int i = 0; i < n_tile; ++i)
+            for (int j = tile_ids[i] * ts; j < (tile_ids[i] + 1) * ts && j < g; ++j) {
+                gene_sum[j] = hs[j];
+                gene_sumsq[j] = hq[j];
+            }
+    d_w.release();
+    d_tiles.release();
+    d_mean.release();
+    return rc;
+}
+
 // ---- downstream analyses of one trait's score matrix (downstream.cu) ------------------------------
 int scdrs_ds_set_scores(scdrs_ctx* c, int64_t n_cell, int32_t ncol, const void* frame, int32_t is_f32,
                         int64_t n_elem, int64_t row_stride, int64_t col_stride, const int32_t* cols) {

@@ -184,6 +184,13 @@ int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, int c
                     double* dev_gsum, double* dev_gsumsq, double* dev_csum, double* dev_csumsq);
 
 int gene_mean_xtc(scdrs_ctx* c, int k, const double* dev_cov, float* dev_gmean32, double* dev_xtc);
+int gene_stats_exact(scdrs_ctx* c, int transform, const double* dev_cell_w, int center, double denom, int n_tile_sel,
+                     const int32_t* dev_tile_ids, const double* dev_mean_in, double* dev_gsum, double* dev_gsumsq);
+int gene_tile_size();
+
+// ---- stats_par.cu ---------------------------------------------------------------------------
+int gene_moments(scdrs_ctx* c, int mode, int k, const double* d_cov, const double* d_w, double* d_out);
+int gene_expm1_implicit(scdrs_ctx* c, const double* d_shift, const double* d_w, double* d_out);
 
 // ---- counts_pp.cu ---------------------------------------------------------------------------
 int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells, int do_norm, double target_sum,

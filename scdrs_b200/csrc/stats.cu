@@ -144,13 +144,16 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
                       const float* __restrict__ data, const uint32_t* __restrict__ tptr,
                       const double* __restrict__ cov_mat,
                       const double* __restrict__ cov_beta, const double* __restrict__ gene_mean,
-                      const double* __restrict__ cell_w, double* __restrict__ gsum,
+                      const double* __restrict__ cell_w, const int32_t* __restrict__ tile_ids,
+                      const double* __restrict__ mean_in, double* __restrict__ gsum,
                       double* __restrict__ gsq) {
     extern __shared__ double sdyn[];                 // [k][kGeneTile] covariate effects, then [kGeneTile] mu
     __shared__ float xt[kSeqRows][kGeneTile + 1];
     __shared__ double tt[2][kSeqRows][kGeneTile];
     const bool owner = threadIdx.x < kGeneTile;
-    const int g0 = blockIdx.x * kGeneTile;
+    // all gene tiles, or the listed ones (the exact-order recomputation of a few genes)
+    const int tile_id = tile_ids != nullptr ? tile_ids[blockIdx.x] : (int)blockIdx.x;
+    const int g0 = tile_id * kGeneTile;
     const int g = g0 + (int)threadIdx.x;
     const bool ok = owner && g < n_gene;
     double* smu = sdyn + (size_t)k * kGeneTile;
@@ -168,7 +171,7 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
         const int nr = (int)((n_cell - r0) < kSeqRows ? (n_cell - r0) : kSeqRows);
         for (int i = xid; i < kSeqRows * (kGeneTile + 1); i += kSeqXform) (&xt[0][0])[i] = 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(kSeqXform));
-        stage_rows(xt, xid, kSeqXform, r0, nr, g0, blockIdx.x, n_cell, indptr, indices, data, tptr);
+        stage_rows(xt, xid, kSeqXform, r0, nr, g0, tile_id, n_cell, indptr, indices, data, tptr);
         asm volatile("bar.sync 1, %0;" ::"n"(kSeqXform));
         for (int p = xid; p < nr * kGeneTile; p += kSeqXform) {
             const int r = p / kGeneTile, gi = p % kGeneTile;
@@ -183,9 +186,11 @@ stats_gene_seq_kernel(int64_t n_cell, int n_gene, int k, int center, double deno
         }
     };
 
+    // mean_in: the centred pass alone, around a mean supplied by the caller (cells sharded over several GPUs: the
+    // mean is that of all shards)
     const int n_pass = center ? 2 : 1;
-    double s = 0.0, q = 0.0, mean = 0.0;
-    for (int pass = 0; pass < n_pass; ++pass) {
+    double s = 0.0, q = 0.0, mean = (mean_in != nullptr && ok) ? mean_in[g] : 0.0;
+    for (int pass = (mean_in != nullptr && center) ? 1 : 0; pass < n_pass; ++pass) {
         if (!owner) produce(0, 0);
         __syncthreads();
         for (int64_t rt = 0; rt < n_rt; ++rt) {
@@ -366,9 +371,62 @@ stats_dense_cell_kernel(int64_t n_cell, int n_gene, int k, const double* __restr
     }
 }
 
+// ---- dense part of the per-cell statistics by algebra (identity transform) ---------------------------
+// sum_g b = C_c . (sum_g B_g) + sum_g mu_g;  sum_g b^2 = C_c' (sum_g B_g B_g') C_c + 2 C_c . (sum_g mu_g B_g) + sum_g mu_g^2
+// side[]: [k] sum B, [k*k] sum B B', [k] sum mu B, [1] sum mu, [1] sum mu^2 -- one block, fixed order.
+__global__ void __launch_bounds__(256)
+gene_side_sums_kernel(int n_gene, int k, const double* __restrict__ cov_beta, const double* __restrict__ gene_mean,
+                      double* __restrict__ side) {
+    __shared__ double sh[256];
+    const int n_q = k + k * k + k + 2;
+    for (int q = 0; q < n_q; ++q) {
+        double part = 0.0;
+        for (int g = threadIdx.x; g < n_gene; g += 256) {
+            const double* b = cov_beta + (size_t)g * k;
+            const double mu = gene_mean[g];
+            double v;
+            if (q < k) v = b[q];
+            else if (q < k + k * k) v = b[(q - k) / k] * b[(q - k) % k];
+            else if (q < 2 * k + k * k) v = mu * b[q - k - k * k];
+            else if (q == 2 * k + k * k) v = mu;
+            else v = mu * mu;
+            part += v;
+        }
+        sh[threadIdx.x] = part;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) side[q] = sh[0];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+stats_dense_cell_alg_kernel(int64_t n_cell, int k, const double* __restrict__ cov_mat, const double* __restrict__ side,
+                            double* __restrict__ csum, double* __restrict__ csq) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n_cell) return;
+    const double* c = cov_mat + row * k;
+    const double* s_b = side;
+    const double* s_bb = side + k;
+    const double* s_mub = side + k + k * k;
+    double s = side[2 * k + k * k], q = side[2 * k + k * k + 1];
+    for (int i = 0; i < k; ++i) {
+        s = fma(c[i], s_b[i], s);
+        double row_i = 2.0 * s_mub[i];
+        for (int j = 0; j < k; ++j) row_i = fma(s_bb[i * k + j], c[j], row_i);
+        q = fma(c[i], row_i, q);
+    }
+    csum[row] = s;
+    csq[row] = q;
+}
+
 template <int TRANSFORM>
 static int run_stats(scdrs_ctx* c, const double* dev_cell_w, int center, double denom, double* gsum,
-                     double* gsq, double* csum, double* csq) {
+                     double* gsq, double* csum, double* csq, int n_tile_sel = 0, const int32_t* dev_tile_ids = nullptr,
+                     const double* dev_mean_in = nullptr) {
     const int k = c->k, n_gene = c->n_gene;
     const int64_t n_cell = c->n_cell;
     if (gsum != nullptr) {
@@ -377,18 +435,28 @@ static int run_stats(scdrs_ctx* c, const double* dev_cell_w, int center, double 
         SCDRS_CHECK(smem <= 150 * 1024, "too many covariates (%d) for the statistics kernel", k);
         SCDRS_CUDA(cudaFuncSetAttribute(stats_gene_seq_kernel<TRANSFORM>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-        SCDRS_TRY(ensure_tile_ptr(c));
-        stats_gene_seq_kernel<TRANSFORM><<<tiles, kSeqThreads, smem, c->stream>>>(
+        // a few listed tiles: rows are searched instead of building the (n_tile + 1) x n_cell table of tile starts
+        if (dev_tile_ids == nullptr) SCDRS_TRY(ensure_tile_ptr(c));
+        const bool table = dev_tile_ids == nullptr && c->tile_ptr_valid;
+        stats_gene_seq_kernel<TRANSFORM><<<dev_tile_ids != nullptr ? n_tile_sel : tiles, kSeqThreads, smem, c->stream>>>(
             n_cell, n_gene, k, center, denom, c->indptr, c->indices, c->data,
-            c->tile_ptr_valid ? c->tile_ptr.as<uint32_t>() : nullptr, c->cov_mat.as<double>(),
-            c->cov_beta.as<double>(), c->gene_mean.as<double>(), dev_cell_w, gsum, gsq);
+            table ? c->tile_ptr.as<uint32_t>() : nullptr, c->cov_mat.as<double>(),
+            c->cov_beta.as<double>(), c->gene_mean.as<double>(), dev_cell_w, dev_tile_ids, dev_mean_in, gsum, gsq);
         SCDRS_LAUNCH_CHECK(c);
     }
     if (csum != nullptr) {
         int64_t grid = (n_cell + 7) / 8;
         if (grid > kNumSM * 8) grid = kNumSM * 8;
         if (grid < 1) grid = 1;
-        if (k > 0) {
+        if (k > 0 && TRANSFORM == 0) {
+            SCDRS_TRY(c->scan_tmp.reserve((size_t)(2 * k + k * k + 2) * sizeof(double)));
+            gene_side_sums_kernel<<<1, 256, 0, c->stream>>>(n_gene, k, c->cov_beta.as<double>(), c->gene_mean.as<double>(),
+                                                            c->scan_tmp.as<double>());
+            SCDRS_LAUNCH_CHECK(c);
+            stats_dense_cell_alg_kernel<<<(unsigned)((n_cell + 255) / 256), 256, 0, c->stream>>>(
+                n_cell, k, c->cov_mat.as<double>(), c->scan_tmp.as<double>(), csum, csq);
+            SCDRS_LAUNCH_CHECK(c);
+        } else if (k > 0) {
             stats_dense_cell_kernel<TRANSFORM><<<(unsigned)grid, 256, 0, c->stream>>>(
                 n_cell, n_gene, k, c->cov_mat.as<double>(), c->cov_beta.as<double>(),
                 c->gene_mean.as<double>(), csum, csq);
@@ -415,5 +483,18 @@ int gene_cell_stats(scdrs_ctx* c, int transform, const double* dev_cell_w, int c
     if (transform == 0) return run_stats<0>(c, dev_cell_w, center, denom, dev_gsum, dev_gsumsq, dev_csum, dev_csumsq);
     return run_stats<1>(c, dev_cell_w, center, denom, dev_gsum, dev_gsumsq, dev_csum, dev_csumsq);
 }
+
+// the sequential (numpy-order) per-gene sums for the listed gene tiles only
+int gene_stats_exact(scdrs_ctx* c, int transform, const double* dev_cell_w, int center, double denom, int n_tile_sel,
+                     const int32_t* dev_tile_ids, const double* dev_mean_in, double* dev_gsum, double* dev_gsumsq) {
+    SCDRS_CHECK(c->indptr != nullptr, "no expression matrix set (call scdrs_set_csr_* first)");
+    SCDRS_CHECK(transform == 0 || transform == 1, "transform must be 0 (identity) or 1 (expm1)");
+    SCDRS_CHECK(n_tile_sel >= 1 && dev_tile_ids != nullptr, "no gene tiles listed");
+    if (transform == 0)
+        return run_stats<0>(c, dev_cell_w, center, denom, dev_gsum, dev_gsumsq, nullptr, nullptr, n_tile_sel, dev_tile_ids, dev_mean_in);
+    return run_stats<1>(c, dev_cell_w, center, denom, dev_gsum, dev_gsumsq, nullptr, nullptr, n_tile_sel, dev_tile_ids, dev_mean_in);
+}
+
+int gene_tile_size() { return kGeneTile; }
 
 }  // namespace scdrs

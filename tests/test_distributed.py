@@ -200,3 +200,86 @@ def test_control_sets_drawn_by_one_rank_reach_all_ranks(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_run_bcast, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "bcast_ok_%d" % r)) for r in range(2))
+
+
+# ---- distributed preprocess: gene-level parameters from the cells of all ranks ------------------------------
+def _pp_problem():
+    from scdrs_b200 import synth
+
+    adata, cov = synth.make_adata(420, 700, density=0.15, seed=17, n_group=6)
+    cov["batch"] = np.where(np.arange(420) % 3 == 0, "a", np.where(np.arange(420) % 3 == 1, "b", "c"))   # categorical
+    cov.loc[cov.index[5], "age"] = np.nan                                                                     # one missing value
+    cov = cov.drop(columns=["const"])           # preprocess has to add SCDRS_CONST itself ...
+    cov["n_genes"] -= cov["n_genes"].mean()     # ... because nothing left spans the constant
+    return adata, cov
+
+
+def _run_pp_rank(rank, world, port, out_dir, adj_prop):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pandas as pd
+
+        from fake_device import NumpyStatsState
+        from scdrs_b200 import pp
+        from scdrs_b200.anndata_lite import AnnData
+
+        pp.get_state = lambda adata, device=None: NumpyStatsState(adata)         # numpy stand-in for the device calls
+        adata, cov = _pp_problem()
+        bounds = [0, 150, 420] if world == 2 else [0, 420]                       # ragged shards; "c"-heavy second shard
+        lo, hi = bounds[rank], bounds[rank + 1]
+        shard = AnnData(adata.X[lo:hi].tocsr(), adata.obs.iloc[lo:hi].copy(), adata.var.copy())
+        pp.preprocess(shard, cov=cov.iloc[lo:hi], adj_prop="cell_type" if adj_prop else None, sharded=world > 1)
+        p = shard.uns["SCDRS_PARAM"]
+        gs = p["GENE_STATS"]
+        np.savez(os.path.join(out_dir, "pp_rank%d_of%d_%d.npz" % (rank, world, int(adj_prop))), lo=lo, hi=hi,
+                 gs=gs[["mean", "var", "var_tech", "ct_mean", "ct_var", "ct_var_tech"]].values.astype(np.float64),
+                 bins=np.array([str(x) for x in gs["mean_var"].values]), beta=p["COV_BETA"].values, mu=p["COV_GENE_MEAN"].values,
+                 cov_cols=np.array([str(x) for x in p["COV_MAT"].columns]), cov_mat=p["COV_MAT"].values,
+                 cell=p["CELL_STATS"].values.astype(np.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("adj_prop", [False, True])
+def test_sharded_preprocess_equals_unsharded(tmp_path, adj_prop):
+    """preprocess(..., sharded=True) on two ragged shards: GENE_STATS (bins included), COV_BETA and COV_GENE_MEAN are
+    those of the whole atlas and identical on both ranks; COV_MAT / CELL_STATS are the rank's rows of the unsharded
+    result.  Categorical covariates whose levels differ between shards, a missing value and the cell-type weights of
+    adj_prop go through the same sums over ranks.  (Device reductions answered by a numpy stand-in.)"""
+    import socket
+
+    for world in (2, 1):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        mp.spawn(_run_pp_rank, args=(world, port, str(tmp_path), adj_prop), nprocs=world, join=True)
+    full = np.load(os.path.join(str(tmp_path), "pp_rank0_of1_%d.npz" % int(adj_prop)))
+    parts = [np.load(os.path.join(str(tmp_path), "pp_rank%d_of2_%d.npz" % (r, int(adj_prop)))) for r in range(2)]
+    for key in ("gs", "beta", "mu"):
+        assert np.array_equal(parts[0][key], parts[1][key]), key                   # identical bits on every rank
+        assert np.allclose(parts[0][key], full[key], rtol=1e-9, atol=1e-12), key   # and the unsharded values
+    assert np.array_equal(parts[0]["bins"], parts[1]["bins"]) and np.array_equal(parts[0]["bins"], full["bins"])
+    assert list(parts[0]["cov_cols"]) == list(full["cov_cols"]) and "SCDRS_CONST" in list(full["cov_cols"])
+    assert np.allclose(np.concatenate([p["cov_mat"] for p in parts]), full["cov_mat"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.concatenate([p["cell"] for p in parts]), full["cell"], rtol=1e-9, atol=1e-12)
+
+
+def test_preprocess_host_algebra_against_oracle(monkeypatch):
+    """The identities that turn per-gene moments into the mean / variance of X + COV_MAT*COV_BETA + COV_GENE_MEAN
+    (scdrs_b200/pp.py:_gene_mean_var_fast) against the oracle's dense restatement of scdrs/pp.py:353-373."""
+    from fake_device import NumpyStatsState
+    from oracle import scdrs_oracle as orc
+    from scdrs_b200 import pp, synth
+    from scdrs_b200.loess1d import loess
+
+    monkeypatch.setattr(pp, "get_state", lambda adata, device=None: NumpyStatsState(adata))
+    for adj in (None, "cell_type"):
+        for use_cov in (True, False):
+            adata, cov = synth.make_adata(300, 500, density=0.2, seed=23, n_group=5)
+            ref = adata.copy()
+            pp.preprocess(adata, cov=cov if use_cov else None, adj_prop=adj)
+            orc.preprocess(ref, cov=cov if use_cov else None, adj_prop=adj, loess_impl=loess)
+            g, r = adata.uns["SCDRS_PARAM"]["GENE_STATS"], ref.uns["SCDRS_PARAM"]["GENE_STATS"]
+            for c in ["mean", "var", "ct_mean", "ct_var", "var_tech"]:
+                assert np.allclose(g[c].values.astype(float), r[c].values.astype(float), rtol=2e-6, atol=1e-9), (adj, use_cov, c)
+            assert (g["mean_var"].astype(str).values != r["mean_var"].astype(str).values).sum() <= 2
