@@ -156,9 +156,11 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
         print("First 3 elements for '%s': %s, %s" % (gs, str(dict_gs[gs][0][:3]), str(dict_gs[gs][1][:3])))
     print("")
 
+    t_loaded = time.time()
     print("Preprocessing:")
     scdrs_b200.preprocess(adata, cov=df_cov, adj_prop=adj_prop, n_mean_bin=20, n_var_bin=20, copy=False)
     print("")
+    t_preprocessed = time.time()
 
     print("Computing scDRS score:")
     os.makedirs(out_folder, exist_ok=True)
@@ -178,9 +180,25 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
               % (trait, len(dict_gs[trait][0]), (v_fdr < 0.1).sum(), df_res.shape[0], (v_fdr < 0.2).sum(),
                  df_res.shape[0], time.time() - sys_start_time))
 
-    scdrs_b200.score_traits(adata, dict_gs, ctrl_match_key=ctrl_match_opt, n_ctrl=n_ctrl, weight_opt=weight_opt,
-                            return_ctrl_raw_score=flag_return_ctrl_raw_score,
-                            return_ctrl_norm_score=flag_return_ctrl_norm_score, min_genes=10, on_result=write)
+    t_write = [0.0]
+    write_inner = write
+
+    def write(trait, df_res):               # noqa: F811 -- timed wrapper around the writer above
+        t0 = time.time()
+        write_inner(trait, df_res)
+        t_write[0] += time.time() - t0
+
+    scored = scdrs_b200.score_traits(adata, dict_gs, ctrl_match_key=ctrl_match_opt, n_ctrl=n_ctrl,
+                                     weight_opt=weight_opt, return_ctrl_raw_score=flag_return_ctrl_raw_score,
+                                     return_ctrl_norm_score=flag_return_ctrl_norm_score, min_genes=10,
+                                     on_result=write)
+    t_end = time.time()
+    n_scored = max(1, len(scored))
+    # scoring and file writing overlap (the writer runs beside the GPU): "score+write" is their wall clock
+    print("Timing: load=%.2fs preprocess=%.2fs score+write=%.2fs (%.3fs per trait over %d traits; "
+          "%.3fs per trait inside the score-file writer) total=%.2fs"
+          % (t_loaded - sys_start_time, t_preprocessed - t_loaded, t_end - t_preprocessed,
+             (t_end - t_preprocessed) / n_scored, len(scored), t_write[0] / n_scored, t_end - sys_start_time))
 
 
 def perform_downstream(h5ad_file, score_file, out_folder, group_analysis=None, corr_analysis=None,

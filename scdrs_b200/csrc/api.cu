@@ -63,10 +63,10 @@ static int h2d(scdrs_ctx* c, DevBuf& buf, const void* host, size_t bytes) {
 // data is on the device.
 namespace {
 constexpr size_t kUpChunk = (size_t)8 << 20;
-constexpr int kUpThreads = 4;
+constexpr int kUpThreads = 8;
 struct Uploader {
-    void* pin[kUpThreads] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t st[kUpThreads] = {nullptr, nullptr, nullptr, nullptr};
+    void* pin[kUpThreads] = {};
+    cudaStream_t st[kUpThreads] = {};
     int device = -1;
     std::mutex mu;
 };

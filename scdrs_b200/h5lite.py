@@ -327,3 +327,162 @@ class File(Group):
             raise H5Error("object at %d is neither an old-style group nor a dataset" % addr)
         self._cache[addr] = obj
         return obj
+
+
+# ------------------------------------------------------------------------------------------------------
+# Minimal writer: enough of HDF5 (superblock v0, v1 object headers, old-style groups, contiguous datasets,
+# fixed-length strings, v1 attributes) to put an AnnData-like object on disk in the ``.h5ad`` layout the reader
+# above -- and h5py / anndata -- understand.  Used to build synthetic benchmark inputs for ``scdrs compute-score``
+# (tests/scripts/bench_cli.py); host-side I/O glue.
+# ------------------------------------------------------------------------------------------------------
+_LEAF_K = 64          # symbol-table node capacity 2 * K = 128 links per group
+
+
+class _Out:
+    def __init__(self, fh):
+        self.fh, self.pos = fh, 0
+
+    def write(self, data):
+        """Append 8-byte aligned; returns the address."""
+        pad = (-self.pos) % 8
+        if pad:
+            self.fh.write(b"\0" * pad)
+            self.pos += pad
+        addr = self.pos
+        self.fh.write(data)
+        self.pos += len(data)
+        return addr
+
+
+def _msg(mtype, body):
+    body = body + b"\0" * ((-len(body)) % 8)
+    return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+
+def _dtype_body(dt):
+    """Datatype message body of a numpy dtype (integers, floats) or ('S', n) fixed strings."""
+    if isinstance(dt, tuple):
+        return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, dt[1])                  # null-terminated ASCII/UTF-8 bytes
+    dt = np.dtype(dt)
+    if dt.kind in "iu":
+        return struct.pack("<BBBBIHH", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, dt.itemsize, 0, 8 * dt.itemsize)
+    if dt == np.float32:
+        return struct.pack("<BBBBIHHBBBBI", 0x11, 0x20, 31, 0, 4, 0, 32, 23, 8, 0, 23, 127)
+    if dt == np.float64:
+        return struct.pack("<BBBBIHHBBBBI", 0x11, 0x20, 63, 0, 8, 0, 64, 52, 11, 0, 52, 1023)
+    raise H5Error("cannot write dtype %s" % dt)
+
+
+def _space_body(shape):
+    return struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(s)) for s in shape)
+
+
+def _as_storable(value):
+    """(raw bytes, dtype spec, shape) of a dataset / attribute value."""
+    if isinstance(value, str):
+        raw = value.encode("utf-8")
+        return raw + b"\0", ("S", len(raw) + 1), ()
+    arr = np.asarray(value)
+    if arr.dtype.kind in "OUS":
+        enc = [str(x).encode("utf-8") for x in arr.reshape(-1)]
+        width = max([len(e) for e in enc] + [0]) + 1
+        fixed = np.array(enc, dtype="S%d" % width)
+        return fixed.tobytes(), ("S", width), arr.shape
+    if arr.dtype == bool:
+        arr = arr.astype(np.int8)
+    arr = np.ascontiguousarray(arr)
+    return arr, arr.dtype, arr.shape
+
+
+def _attr_msg(name, value):
+    raw, dt, shape = _as_storable(value)
+    raw = raw if isinstance(raw, bytes) else raw.tobytes()
+    nm = name.encode("utf-8") + b"\0"
+    dtb, spb = _dtype_body(dt), _space_body(shape)
+    pad = lambda b: b + b"\0" * ((-len(b)) % 8)              # noqa: E731
+    body = struct.pack("<BBHHH", 1, 0, len(nm), len(dtb), len(spb)) + pad(nm) + pad(dtb) + pad(spb) + raw
+    return _msg(0x0C, body)
+
+
+def _object_header(out, msgs):
+    data = b"".join(msgs)
+    return out.write(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(data)) + data)
+
+
+def _write_dataset(out, value, attrs=None):
+    raw, dt, shape = _as_storable(value)
+    nbytes = len(raw) if isinstance(raw, bytes) else raw.nbytes
+    addr = out.write(raw if isinstance(raw, bytes) else memoryview(raw).cast("B")) if nbytes else UNDEF
+    msgs = [_msg(0x01, _space_body(shape)), _msg(0x03, _dtype_body(dt)),
+            _msg(0x08, struct.pack("<BBQQ", 3, 1, addr, nbytes))]
+    msgs += [_attr_msg(k, v) for k, v in (attrs or {}).items()]
+    return _object_header(out, msgs)
+
+
+def _write_group(out, links, attrs=None):
+    """links: {name: object header address}.  Returns (object header address, b-tree address, heap address)."""
+    if len(links) > 2 * _LEAF_K:
+        raise H5Error("h5lite writes at most %d links per group" % (2 * _LEAF_K))
+    names = sorted(links)
+    heap_data, offs = bytearray(b"\0" * 8), {}
+    for nm in names:
+        offs[nm] = len(heap_data)
+        e = nm.encode("utf-8") + b"\0"
+        heap_data += e + b"\0" * ((-len(e)) % 8)
+    heap_data += b"\0" * 16                                   # one free block (size 16) so the free list is valid
+    free_off = len(heap_data) - 16
+    struct.pack_into("<QQ", heap_data, free_off, 1, 16)       # next free = 1 (none), size
+    dseg = out.write(bytes(heap_data))
+    heap = out.write(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, dseg))
+    snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(names)))
+    for nm in names:
+        snod += struct.pack("<QQII16x", offs[nm], links[nm], 0, 0)
+    snod += b"\0" * (40 * (2 * _LEAF_K - len(names)))
+    snod_addr = out.write(bytes(snod))
+    k_int = 16
+    tree = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF))
+    tree += struct.pack("<QQQ", 0, snod_addr, offs[names[-1]] if names else 0)
+    tree += b"\0" * (8 * (2 * k_int + 1) + 8 * 2 * k_int - 24)
+    btree = out.write(bytes(tree))
+    msgs = [_msg(0x11, struct.pack("<QQ", btree, heap))] + [_attr_msg(k, v) for k, v in (attrs or {}).items()]
+    return _object_header(out, msgs), btree, heap
+
+
+def _write_frame(out, df):
+    links = {"_index": _write_dataset(out, np.asarray(df.index, dtype=object))}
+    for c in df.columns:
+        links[str(c)] = _write_dataset(out, df[c].values)
+    attrs = {"_index": "_index", "encoding-type": "dataframe", "encoding-version": "0.1.0"}
+    if len(df.columns):
+        attrs["column-order"] = np.array([str(c) for c in df.columns], dtype=object)
+    return _write_group(out, links, attrs)[0]
+
+
+def write_h5ad(path, adata):
+    """Write X (CSR / CSC / dense), obs and var of an AnnData-like object as an ``.h5ad`` file (obs / var columns:
+    numbers or strings)."""
+    from scipy import sparse
+
+    with open(path, "wb") as fh:
+        out = _Out(fh)
+        out.write(b"\0" * 96)                                  # superblock, filled in at the end
+        X = adata.X
+        if sparse.issparse(X):
+            fmt = "csc_matrix" if isinstance(X, sparse.csc_matrix) else "csr_matrix"
+            if fmt == "csr_matrix" and not isinstance(X, sparse.csr_matrix):
+                X = sparse.csr_matrix(X)
+            x_links = {"data": _write_dataset(out, X.data), "indices": _write_dataset(out, X.indices),
+                       "indptr": _write_dataset(out, X.indptr)}
+            x_addr = _write_group(out, x_links, {"encoding-type": fmt, "encoding-version": "0.1.0",
+                                                 "shape": np.asarray(X.shape, dtype=np.int64)})[0]
+        else:
+            x_addr = _write_dataset(out, np.asarray(X))
+        root_links = {"X": x_addr, "obs": _write_frame(out, adata.obs), "var": _write_frame(out, adata.var)}
+        root, btree, heap = _write_group(out, root_links, {"encoding-type": "anndata", "encoding-version": "0.1.0"})
+        eof = out.write(b"")
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _LEAF_K, 16, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", btree, heap)
+        assert len(sb) == 96
+        fh.seek(0)
+        fh.write(sb)

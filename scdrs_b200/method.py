@@ -242,25 +242,22 @@ def _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_sc
     with np.errstate(divide="ignore"):
         nlog10_pooled_p = -np.log10(pooled_p)                                 # :207
     pooled_z = -sp.stats.norm.ppf(pooled_p).clip(min=-10, max=10)             # :208
-    dic_res = {
-        "raw_score": out["raw_score"],
-        "norm_score": out["norm_score"],
-        "mc_pval": mc_p,
-        "pval": pooled_p,
-        "nlog10_pval": nlog10_pooled_p,
-        "zscore": pooled_z,
-    }
-    df_res = pd.DataFrame(index=adata.obs.index, data=dic_res, dtype=np.float32)
-    blocks = [df_res]
+    # one float32 block [n_cell x (6 [+ n_ctrl] [+ n_ctrl])]: the frame is a view of it, and so is what the score
+    # file writer reads (pd.concat of separate frames would copy the control matrix twice more)
+    cols = ["raw_score", "norm_score", "mc_pval", "pval", "nlog10_pval", "zscore"]
+    n_extra = (n_ctrl if return_ctrl_raw_score else 0) + (n_ctrl if return_ctrl_norm_score else 0)
+    full = np.empty((n_cell, 6 + n_extra), dtype=np.float32)
+    for j, v in enumerate((out["raw_score"], out["norm_score"], mc_p, pooled_p, nlog10_pooled_p, pooled_z)):
+        full[:, j] = v
+    o = 6
     if return_ctrl_raw_score:
-        blocks.append(pd.DataFrame(out["ctrl_raw"], index=adata.obs.index,
-                                   columns=["ctrl_raw_score_%d" % i for i in range(n_ctrl)]))
+        full[:, o:o + n_ctrl] = out["ctrl_raw"]
+        cols += ["ctrl_raw_score_%d" % i for i in range(n_ctrl)]
+        o += n_ctrl
     if return_ctrl_norm_score:
-        blocks.append(pd.DataFrame(out["ctrl_norm"], index=adata.obs.index,
-                                   columns=["ctrl_norm_score_%d" % i for i in range(n_ctrl)]))
-    if len(blocks) > 1:
-        df_res = pd.concat(blocks, axis=1)
-    return df_res
+        full[:, o:o + n_ctrl] = out["ctrl_norm"]
+        cols += ["ctrl_norm_score_%d" % i for i in range(n_ctrl)]
+    return pd.DataFrame(full, index=adata.obs.index, columns=cols, copy=False)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -277,7 +277,9 @@ def test_preprocess_matches_reference_golden_stats(sc, path, exact_order, monkey
     assert set(param) >= {"FLAG_SPARSE", "FLAG_COV", "FLAG_ADJ_PROP", "GENE_STATS", "CELL_STATS"}
     assert list(param["GENE_STATS"].columns) == ["mean", "var", "var_tech", "ct_mean", "ct_var", "ct_var_tech", "mean_var"]
     gs = param["GENE_STATS"]
-    tol = 1e-7 if case["use_cov"] else 2e-5      # reference normal sparse mode accumulates in float32
+    # reference normal sparse mode accumulates in float32; with covariates its float32-accumulated COV_GENE_MEAN (up to
+    # 5e-7 off the exact mean at these sizes) is part of every corrected value, and only the sequential path repeats it
+    tol = (1e-7 if exact_order else 2e-6) if case["use_cov"] else 2e-5
     for c in ["mean", "var", "ct_mean", "ct_var", "var_tech", "ct_var_tech"]:
         assert np.allclose(gs[c].values.astype(float), z["gs_" + c], rtol=max(tol, 1e-5 if "tech" in c else tol), atol=1e-10), c
     n_bin_diff = int((gs["mean_var"].astype(str).values != z["gs_mean_var"]).sum())
