@@ -137,6 +137,14 @@ int scdrs_score_trait_submit(scdrs_ctx* ctx, int32_t n_ctrl, int32_t n_s, int32_
                              int32_t* slot_out);
 int scdrs_score_trait_collect(scdrs_ctx* ctx, int32_t slot, double* raw_score, float* norm_score,
                               int32_t* mc_count, int64_t* ge_count, float* ctrl_raw, float* ctrl_norm);
+/* Text output (the score-file writer's fast path): after scdrs_ctx_set_text_output(ctx, 1), a trait submitted with
+ * want_ctrl_norm != 0 keeps its normalised control scores on the device and turns them there into the text pandas
+ * writes for them -- one 16-byte slot per value, see scdrs_write_score_gz_slots -- instead of downloading n_cell x
+ * n_ctrl floats for host threads to print.  After the trait was collected, scdrs_slot_text returns the pinned host
+ * block [n_cell x n_ctrl x 16] of its slot; it stays valid until the next submit that takes this slot (the one
+ * after next).  The float matrix is then not available from scdrs_score_trait_collect (pass ctrl_norm = NULL). */
+int scdrs_ctx_set_text_output(scdrs_ctx* ctx, int32_t on);
+int scdrs_slot_text(scdrs_ctx* ctx, int32_t slot, const void** text, int64_t* n_bytes);
 
 /* The same split for the phase-by-phase (multi-GPU) driver: phase 1 with the control sets already in
  * device memory (dev_ctrl_genes[n_ctrl x n_s_ctrl], e.g. the receive buffer of a broadcast; the small
@@ -256,8 +264,19 @@ int scdrs_select_ctrl_state(uint32_t seed, int32_t n_bin, const int32_t* bin_ptr
 int scdrs_write_score_gz(const char* path, const char* header, int64_t n_row, int32_t n_col,
                          const char* names, const int64_t* name_off, const float* values,
                          int32_t n_thread, int32_t level);
+/* The same file when the GPU has already formatted the trailing n_slot_col columns (the normalised control scores):
+ * lead[n_row x n_lead] float32 are printed by the host threads, slots[n_row x n_slot_col x 16] are the text slots of
+ * scdrs_slot_text -- text in bytes 0 .. len-1 (at most 15), len in byte 15 -- and are only copied. */
+int scdrs_write_score_gz_slots(const char* path, const char* header, int64_t n_row, const char* names,
+                               const int64_t* name_off, int32_t n_lead, const float* lead, int32_t n_slot_col,
+                               const uint8_t* slots, int32_t n_thread, int32_t level);
 /* one float32 in that text format into out64 (NUL-terminated); returns its length */
 int scdrs_format_f32(float v, char* out64);
+/* The __host__ __device__ formatter the GPU uses for the control-score block of a .full_score.gz file, and its
+ * self-test against scdrs_format_f32 over the float32 bit patterns [first, first + count) (returns the number of
+ * mismatches; the whole 2^32 range takes about a minute on 32 threads). */
+int scdrs_format_f32_shortest(float v, char* out64);
+int64_t scdrs_selftest_format(uint32_t first, uint64_t count, int32_t n_thread, uint32_t* bad_bits);
 
 #ifdef __cplusplus
 }

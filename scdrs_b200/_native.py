@@ -84,7 +84,13 @@ SIGNATURES = {
                                           C.c_int32, C.c_void_p, C.c_void_p]),
     "scdrs_write_score_gz": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_int32]),
+    "scdrs_write_score_gz_slots": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                             C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "scdrs_ctx_set_text_output": (C.c_int, [C.c_void_p, C.c_int32]),
+    "scdrs_slot_text": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "scdrs_format_f32": (C.c_int, [C.c_float, C.c_char_p]),
+    "scdrs_format_f32_shortest": (C.c_int, [C.c_float, C.c_char_p]),
+    "scdrs_selftest_format": (C.c_int64, [C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32)]),
 }
 
 WEIGHT_OPT = {"uniform": 0, "vs": 1, "inv_std": 2}
@@ -264,10 +270,25 @@ class Context:
             self._h, n_ctrl, n_s, n_sc, ptr(trait_genes), ptr(trait_gw), ptr(ctrl_genes), ptr(ctrl_gw),
             WEIGHT_OPT[weight_opt], int(bool(use_var_ratio)), int(bool(want_ctrl_raw)), int(bool(want_ctrl_norm)),
             C.byref(slot)))
-        return (slot.value, n_ctrl, bool(want_ctrl_raw), bool(want_ctrl_norm))
+        as_text = bool(want_ctrl_norm) and getattr(self, "text_output", False) and n_ctrl > 0
+        return (slot.value, n_ctrl, bool(want_ctrl_raw), bool(want_ctrl_norm) and not as_text, as_text)
+
+    def set_text_output(self, on):
+        """Traits submitted with want_ctrl_norm leave the device as text slots (scdrs_ctx_set_text_output)."""
+        check(self._L.scdrs_ctx_set_text_output(self._h, int(bool(on))))
+        self.text_output = bool(on)
+
+    def slot_text(self, slot, n_ctrl):
+        """uint8 view [n_cell, n_ctrl, 16] of the pinned text block of a collected slot (valid until the submit after next)."""
+        p, nb = C.c_void_p(), C.c_int64()
+        check(self._L.scdrs_slot_text(self._h, int(slot), C.byref(p), C.byref(nb)))
+        assert nb.value == self.n_cell * n_ctrl * 16
+        buf = (C.c_uint8 * nb.value).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.n_cell, n_ctrl, 16)
 
     def score_trait_collect(self, ticket):
-        slot, n_ctrl, want_ctrl_raw, want_ctrl_norm = ticket
+        slot, n_ctrl, want_ctrl_raw, want_ctrl_norm = ticket[:4]
+        as_text = len(ticket) > 4 and ticket[4]
         n = self.n_cell
         out = dict(
             raw_score=np.empty(n, np.float64), norm_score=np.empty(n, np.float32),
@@ -278,6 +299,9 @@ class Context:
         check(self._L.scdrs_score_trait_collect(
             self._h, slot, ptr(out["raw_score"]), ptr(out["norm_score"]), ptr(out["mc_count"]), ptr(out["ge_count"]),
             ptr(out["ctrl_raw"]), ptr(out["ctrl_norm"])))
+        if as_text:
+            out["ctrl_norm_text"] = self.slot_text(slot, n_ctrl)
+            out["slot"] = slot
         return out
 
     # -- phases (device pointers are plain ints) --
@@ -519,6 +543,24 @@ def write_score_gz(path, df, n_thread=None, level=None):
     level = gzip_level() if level is None else level
     check(lib().scdrs_write_score_gz(os.fsencode(path), header.encode("utf-8"), values.shape[0], values.shape[1],
                                      C.cast(buf, C.c_void_p), ptr(off), ptr(values), int(n_thread), int(level)))
+
+
+def write_score_gz_slots(path, df_lead, extra_columns, slots, n_thread=None, level=None):
+    """The score file whose trailing columns the GPU already formatted: ``df_lead`` (float32 frame) is printed by the
+    host threads, ``slots`` uint8 [n_row, n_extra, 16] are copied (scdrs_write_score_gz_slots)."""
+    import os
+
+    values = df_lead.values
+    if values.dtype != np.float32 or not values.flags["C_CONTIGUOUS"]:
+        values = as_c(values, np.float32)
+    assert slots.dtype == np.uint8 and slots.flags["C_CONTIGUOUS"] and slots.shape[0] == values.shape[0]
+    buf, off = _index_blob(df_lead.index)
+    header = "\t".join([df_lead.index.name or ""] + [str(c) for c in df_lead.columns] + list(extra_columns)) + "\n"
+    n_thread = n_thread or max(1, min(32, (os.cpu_count() or 2)))
+    level = gzip_level() if level is None else level
+    check(lib().scdrs_write_score_gz_slots(os.fsencode(path), header.encode("utf-8"), values.shape[0],
+                                           C.cast(buf, C.c_void_p), ptr(off), values.shape[1], ptr(values),
+                                           slots.shape[1], slots.ctypes.data, int(n_thread), int(level)))
 
 
 def format_f32(v):

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscdrs_b200.so")
-SOURCES = ["api.cu", "spmm_score.cu", "spmm_score_fx.cu", "background.cu", "empi_null.cu", "stats.cu", "stats_par.cu", "counts_pp.cu", "downstream.cu", "ctrl_select.cpp", "score_writer.cu"]
+SOURCES = ["api.cu", "spmm_score.cu", "spmm_score_fx.cu", "background.cu", "empi_null.cu", "stats.cu", "stats_par.cu", "counts_pp.cu", "downstream.cu", "ctrl_select.cpp", "score_writer.cu", "score_format.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-pthread", "--expt-relaxed-constexpr",

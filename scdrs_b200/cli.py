@@ -173,7 +173,13 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
         # same bytes (after gunzip) as DataFrame.to_csv(sep="\t", compression="gzip"), written by the
         # multi-threaded formatter/deflater of libscdrs_b200 (bin/scdrs:276-288 of the reference)
         util.write_score_file(os.path.join(out_folder, "%s.score.gz" % trait), df_res.iloc[:, 0:6])
-        if flag_return_ctrl_raw_score | flag_return_ctrl_norm_score:
+        if "ctrl_norm_text" in df_res.attrs:
+            # the control columns were formatted on the GPU (csrc/score_format.cu): only copied and deflated here
+            from scdrs_b200 import _native
+
+            _native.write_score_gz_slots(os.path.join(out_folder, "%s.full_score.gz" % trait), df_res,
+                                         df_res.attrs["ctrl_norm_columns"], df_res.attrs["ctrl_norm_text"])
+        elif flag_return_ctrl_raw_score | flag_return_ctrl_norm_score:
             util.write_score_file(os.path.join(out_folder, "%s.full_score.gz" % trait), df_res)
         v_fdr = util.fdr_bh(df_res["pval"].values)
         print("Trait=%s, n_gene=%d: %d/%d FDR<0.1 cells, %d/%d FDR<0.2 cells (sys_time=%0.1fs)"
@@ -191,7 +197,9 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
     scored = scdrs_b200.score_traits(adata, dict_gs, ctrl_match_key=ctrl_match_opt, n_ctrl=n_ctrl,
                                      weight_opt=weight_opt, return_ctrl_raw_score=flag_return_ctrl_raw_score,
                                      return_ctrl_norm_score=flag_return_ctrl_norm_score, min_genes=10,
-                                     on_result=write)
+                                     on_result=write,
+                                     text_output=(flag_return_ctrl_norm_score and not flag_return_ctrl_raw_score
+                                                  and os.environ.get("SCDRS_B200_TEXT_OUTPUT", "1") != "0"))
     t_end = time.time()
     n_scored = max(1, len(scored))
     # scoring and file writing overlap (the writer runs beside the GPU): "score+write" is their wall clock

@@ -139,7 +139,7 @@ static void release_all(scdrs_ctx* c) {
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
                       &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr,
-                      &c->fx_xq, &c->fx_meta32, &c->ds_S, &c->ds_tmp, &c->ds_pos, &c->ds_M, &c->ds_keys,
+                      &c->fx_xq, &c->fx_meta32, &c->text_slots, &c->ds_S, &c->ds_tmp, &c->ds_pos, &c->ds_M, &c->ds_keys,
                       &c->ds_vals, &c->ds_off, &c->ds_ref, &c->ds_chunk, &c->ds_part};
     for (DevBuf* b : bufs) b->release();
 }
@@ -247,6 +247,7 @@ int scdrs_ctx_destroy(scdrs_ctx* c) {
     for (auto& sl : c->slot) {
         if (sl.pin_in) cudaFreeHost(sl.pin_in);
         if (sl.pin_out) cudaFreeHost(sl.pin_out);
+        if (sl.pin_text) cudaFreeHost(sl.pin_text);
         if (sl.done) cudaEventDestroy(sl.done);
     }
     for (int i = 0; i < 4; ++i)
@@ -530,7 +531,7 @@ int scdrs_score_trait(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctr
     tr.mark("rowstats");
     SCDRS_TRY(scdrs_trait_queries(c, c->x_col2.as<double>(), c->x_colmin.as<double>(), nullptr));
     SCDRS_TRY(trait_count_impl(c, c->query.as<float>(), c->n_cell,
-                               c->x_hist.as<unsigned long long>(), ctrl_norm != nullptr));
+                               c->x_hist.as<unsigned long long>(), ctrl_norm != nullptr || c->force_norm_mat));
     tr.mark("queries+count");
     const int rc = scdrs_trait_finish(c, c->x_hist.as<unsigned long long>(), c->n_cell, 0,
                                       (int64_t)c->n_cell * n_ctrl, raw_score, norm_score, mc_count,
@@ -600,22 +601,37 @@ int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t 
         memcpy(in + o_cw, ctrl_gw, (size_t)n_s_ctrl * 8);
     }
     memcpy(in + o_tw, trait_gw, (size_t)n_s * 8);
-    SlotOut o = slot_layout(nullptr, n, n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
+    // text output: the normalised control scores stay on the device as floats and leave it as 16-byte text slots
+    const bool as_text = c->text_output && want_ctrl_norm != 0 && n_ctrl > 0;
+    const bool norm_f32 = want_ctrl_norm != 0 && !as_text;
+    SlotOut o = slot_layout(nullptr, n, n_ctrl, want_ctrl_raw != 0, norm_f32);
     SCDRS_TRY(pin_reserve(&sl.pin_out, &sl.out_cap, o.bytes));
+    const size_t text_bytes = as_text ? (size_t)n * n_ctrl * 16 : 0;
+    if (as_text) {
+        SCDRS_TRY(pin_reserve(&sl.pin_text, &sl.text_cap, text_bytes + 64));
+        SCDRS_TRY(c->text_slots.reserve(text_bytes));
+    }
     if (!sl.done) SCDRS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-    o = slot_layout(static_cast<char*>(sl.pin_out), n, n_ctrl, want_ctrl_raw != 0, want_ctrl_norm != 0);
+    o = slot_layout(static_cast<char*>(sl.pin_out), n, n_ctrl, want_ctrl_raw != 0, norm_f32);
     c->finish_async = true;
-    const int rc = scdrs_score_trait(c, n_ctrl, n_s, n_s_ctrl, reinterpret_cast<const int32_t*>(in + o_tg),
-                                     reinterpret_cast<const double*>(in + o_tw), reinterpret_cast<const int32_t*>(in + o_cg),
-                                     reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, o.raw, o.norm,
-                                     o.mc, o.ge, o.craw, o.cnorm);
+    c->force_norm_mat = as_text;
+    int rc = scdrs_score_trait(c, n_ctrl, n_s, n_s_ctrl, reinterpret_cast<const int32_t*>(in + o_tg),
+                               reinterpret_cast<const double*>(in + o_tw), reinterpret_cast<const int32_t*>(in + o_cg),
+                               reinterpret_cast<const double*>(in + o_cw), weight_opt, use_var_ratio, o.raw, o.norm,
+                               o.mc, o.ge, o.craw, o.cnorm);
     c->finish_async = false;
+    c->force_norm_mat = false;
     if (rc) return rc;
+    if (as_text) {
+        SCDRS_TRY(format_text_slots(c, (int64_t)n * n_ctrl, c->norm_mat.as<float>(), c->text_slots.p));
+        SCDRS_TRY(d2h(c, sl.pin_text, c->text_slots.p, text_bytes));
+    }
     SCDRS_CUDA(cudaEventRecord(sl.done, c->stream));
     sl.busy = true;
     sl.n_ctrl = n_ctrl;
     sl.ctrl_raw = want_ctrl_raw != 0;
-    sl.ctrl_norm = want_ctrl_norm != 0;
+    sl.ctrl_norm = norm_f32;
+    sl.text = as_text;
     c->next_slot = id ^ 1;
     *slot_out = id;
     return 0;
@@ -640,6 +656,24 @@ int scdrs_score_trait_collect(scdrs_ctx* c, int32_t slot, double* raw_score, flo
     if (mc_count) memcpy(mc_count, o.mc, (size_t)n * 4);
     if (ctrl_raw) memcpy(ctrl_raw, o.craw, mat);
     if (ctrl_norm) memcpy(ctrl_norm, o.cnorm, mat);
+    return 0;
+}
+
+int scdrs_ctx_set_text_output(scdrs_ctx* c, int32_t on) {
+    CTX_GUARD(c);
+    c->text_output = on != 0;
+    return 0;
+}
+
+int scdrs_slot_text(scdrs_ctx* c, int32_t slot, const void** text, int64_t* n_bytes) {
+    CTX_GUARD(c);
+    SCDRS_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+    SCDRS_CHECK(text != nullptr && n_bytes != nullptr, "null pointer");
+    scdrs_ctx::Slot& sl = c->slot[slot];
+    SCDRS_CHECK(!sl.busy, "collect the slot first");
+    SCDRS_CHECK(sl.text && sl.pin_text != nullptr, "the trait in this slot was not submitted with text output");
+    *text = sl.pin_text;
+    *n_bytes = (int64_t)c->n_cell * sl.n_ctrl * 16;
     return 0;
 }
 

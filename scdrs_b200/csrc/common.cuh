@@ -85,9 +85,15 @@ struct scdrs_ctx {
         bool busy = false;
         int32_t n_ctrl = 0;
         bool ctrl_raw = false, ctrl_norm = false;
+        void* pin_text = nullptr;       // text slots of the normalised control scores (score_format.cu)
+        size_t text_cap = 0;
+        bool text = false;
     } slot[2];
     int next_slot = 0;
     bool finish_async = false;      // scdrs_trait_finish leaves the final stream synchronisation to the caller
+    bool text_output = false;       // submit: the control norm scores leave the device as text slots, not floats
+    bool force_norm_mat = false;    // keep the normalised control matrix on the device although nobody downloads it
+    scdrs::DevBuf text_slots;
 
     // downstream analyses (downstream.cu): the score matrix of one trait, [ds_n x ds_ncol] fp64 row-major
     scdrs::DevBuf ds_S, ds_tmp, ds_pos, ds_M, ds_keys, ds_vals, ds_off, ds_ref, ds_chunk, ds_part;
@@ -191,6 +197,9 @@ int gene_tile_size();
 // ---- stats_par.cu ---------------------------------------------------------------------------
 int gene_moments(scdrs_ctx* c, int mode, int k, const double* d_cov, const double* d_w, double* d_out);
 int gene_expm1_implicit(scdrs_ctx* c, const double* d_shift, const double* d_w, double* d_out);
+
+// ---- score_format.cu ------------------------------------------------------------------------
+int format_text_slots(scdrs_ctx* c, int64_t n_val, const float* dev_vals, void* dev_slots);
 
 // ---- counts_pp.cu ---------------------------------------------------------------------------
 int counts_preprocess(scdrs_ctx* c, int do_filter, int min_genes, int min_cells, int do_norm, double target_sum,

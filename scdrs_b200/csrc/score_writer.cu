@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "score_format.cuh"
 
 namespace {
 
@@ -31,11 +32,10 @@ inline char* fmt_f32(char* p, float v) {
         memcpy(p, "inf", 3);
         return p + 3;
     }
-    const long double a = std::fabs((long double)v);
-    if (a == 0.0L || (a >= 1.e-4L && a < 1.e6L)) {
+    const double a = std::fabs((double)v);             // no float lies between the double and the exact 1e-4 / 1e6
+    if (a == 0.0 || (a >= 1.e-4 && a < 1.e6)) {
         auto r = std::to_chars(p, p + 64, v, std::chars_format::fixed);
-        bool has_dot = false;
-        for (char* q = p; q < r.ptr; ++q) has_dot |= (*q == '.');
+        const bool has_dot = memchr(p, '.', (size_t)(r.ptr - p)) != nullptr;
         p = r.ptr;
         if (!has_dot) { *p++ = '.'; *p++ = '0'; }
         return p;
@@ -49,13 +49,13 @@ struct Block {
     std::atomic<int> ready{0};
 };
 
-bool deflate_member(const std::string& text, int level, std::string& out) {
+bool deflate_member(const char* text, size_t n_text, int level, std::string& out) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-    out.resize(deflateBound(&zs, text.size()) + 64);
-    zs.next_in = (Bytef*)text.data();
-    zs.avail_in = (uInt)text.size();
+    out.resize(deflateBound(&zs, n_text) + 64);
+    zs.next_in = (Bytef*)text;
+    zs.avail_in = (uInt)n_text;
     zs.next_out = (Bytef*)out.data();
     zs.avail_out = (uInt)out.size();
     const int rc = deflate(&zs, Z_FINISH);
@@ -72,47 +72,79 @@ extern "C" int scdrs_format_f32(float v, char* out64) {
     return (int)(e - out64);
 }
 
-extern "C" int scdrs_write_score_gz(const char* path, const char* header, int64_t n_row, int32_t n_col,
-                                    const char* names, const int64_t* name_off, const float* values,
-                                    int32_t n_thread, int32_t level) {
-    SCDRS_CHECK(path && header && (n_row == 0 || (names && name_off && values)), "null pointer");
-    SCDRS_CHECK(n_row >= 0 && n_col >= 0, "negative shape");
+// fmt_f32_shortest (the function the GPU formats with) against std::to_chars for the float32 bit patterns
+// [first, first + count): returns the number of mismatches, the first offending pattern in *bad_bits.
+extern "C" int64_t scdrs_selftest_format(uint32_t first, uint64_t count, int32_t n_thread, uint32_t* bad_bits) {
+    if (n_thread < 1) n_thread = 1;
+    std::atomic<int64_t> bad{0};
+    std::atomic<uint32_t> first_bad{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thread; ++t)
+        pool.emplace_back([&, t]() {
+            char a[80], b[80];
+            for (uint64_t i = (uint64_t)t; i < count; i += (uint64_t)n_thread) {
+                const uint32_t bits = first + (uint32_t)i;
+                float v;
+                memcpy(&v, &bits, 4);
+                const int la = (int)(fmt_f32(a, v) - a);
+                const int lb = scdrs::fmt_f32_shortest(v, b);
+                if (la != lb || memcmp(a, b, (size_t)la) != 0) {
+                    if (bad.fetch_add(1) == 0) first_bad.store(bits);
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+    if (bad_bits) *bad_bits = first_bad.load();
+    return bad.load();
+}
+
+extern "C" int scdrs_format_f32_shortest(float v, char* out64) {
+    const int n = scdrs::fmt_f32_shortest(v, out64);
+    out64[n] = 0;
+    return n;
+}
+
+namespace {
+
+// Row blocks of ~4 MB of text are produced by `row_fn(row, p) -> end of the row's fields` (after the row name),
+// deflated as independent gzip members by n_thread threads and written in order.
+template <typename RowFn>
+int write_blocks(const char* path, const char* header, int64_t n_row, const char* names, const int64_t* name_off,
+                 size_t field_bytes_per_row, RowFn row_fn, int32_t n_thread, int32_t level) {
     if (n_thread < 1) n_thread = 1;
     if (level < 0 || level > 9) level = 6;
     FILE* fh = fopen(path, "wb");
     SCDRS_CHECK(fh != nullptr, "cannot open %s for writing", path);
-    // block size: about 4 MB of text per gzip member
-    int64_t rows_per_block = (int64_t)(4 << 20) / ((int64_t)n_col * 11 + 32);
+    int64_t rows_per_block = (int64_t)(4 << 20) / ((int64_t)(field_bytes_per_row * 11 / 16) + 32);
     if (rows_per_block < 16) rows_per_block = 16;
     const int64_t n_block = (n_row + rows_per_block - 1) / rows_per_block;
     std::vector<Block> blocks((size_t)n_block + 1);
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
     auto work = [&]() {
-        std::string text;
+        std::vector<char> text;          // one buffer per thread, written through a raw pointer
         for (;;) {
             const int64_t b = next.fetch_add(1);
             if (b > n_block) return;
-            text.clear();
+            size_t n_text = 0;
             if (b == 0) {
-                text = header;
+                n_text = strlen(header);
+                text.assign(header, header + n_text);
             } else {
                 const int64_t r0 = (b - 1) * rows_per_block;
                 const int64_t r1 = r0 + rows_per_block < n_row ? r0 + rows_per_block : n_row;
-                text.reserve((size_t)(r1 - r0) * ((size_t)n_col * 12 + 48));
-                char buf[80];
+                const size_t cap = (size_t)(name_off[r1] - name_off[r0]) + (size_t)(r1 - r0) * (field_bytes_per_row + 2) + 64;
+                if (text.size() < cap) text.resize(cap);
+                char* p = text.data();
                 for (int64_t r = r0; r < r1; ++r) {
-                    text.append(names + name_off[r], (size_t)(name_off[r + 1] - name_off[r]));
-                    const float* row = values + r * (int64_t)n_col;
-                    for (int j = 0; j < n_col; ++j) {
-                        buf[0] = '\t';
-                        char* e = fmt_f32(buf + 1, row[j]);
-                        text.append(buf, (size_t)(e - buf));
-                    }
-                    text.push_back('\n');
+                    const size_t ln = (size_t)(name_off[r + 1] - name_off[r]);
+                    memcpy(p, names + name_off[r], ln);
+                    p = row_fn(r, p + ln);
+                    *p++ = '\n';
                 }
+                n_text = (size_t)(p - text.data());
             }
-            if (!deflate_member(text, level, blocks[(size_t)b].gz)) failed.store(1);
+            if (!deflate_member(text.data(), n_text, level, blocks[(size_t)b].gz)) failed.store(1);
             blocks[(size_t)b].ready.store(1, std::memory_order_release);
         }
     };
@@ -129,4 +161,47 @@ extern "C" int scdrs_write_score_gz(const char* path, const char* header, int64_
     ok = (fclose(fh) == 0) && ok && !failed.load();
     SCDRS_CHECK(ok, "writing %s failed", path);
     return 0;
+}
+
+}  // namespace
+
+extern "C" int scdrs_write_score_gz(const char* path, const char* header, int64_t n_row, int32_t n_col,
+                                    const char* names, const int64_t* name_off, const float* values,
+                                    int32_t n_thread, int32_t level) {
+    SCDRS_CHECK(path && header && (n_row == 0 || (names && name_off && values)), "null pointer");
+    SCDRS_CHECK(n_row >= 0 && n_col >= 0, "negative shape");
+    auto row_fn = [=](int64_t r, char* p) {
+        const float* row = values + r * (int64_t)n_col;
+        for (int j = 0; j < n_col; ++j) {
+            *p++ = '\t';
+            p = fmt_f32(p, row[j]);
+        }
+        return p;
+    };
+    return write_blocks(path, header, n_row, names, name_off, (size_t)n_col * 16, row_fn, n_thread, level);
+}
+
+// The same file from two sources: n_lead float32 columns formatted here, then n_slot_col columns that the GPU
+// already turned into text slots (score_format.cu: 16 bytes per value, text in bytes 0 .. len-1, len in byte 15).
+extern "C" int scdrs_write_score_gz_slots(const char* path, const char* header, int64_t n_row, const char* names,
+                                          const int64_t* name_off, int32_t n_lead, const float* lead,
+                                          int32_t n_slot_col, const uint8_t* slots, int32_t n_thread, int32_t level) {
+    SCDRS_CHECK(path && header && (n_row == 0 || (names && name_off)), "null pointer");
+    SCDRS_CHECK(n_row >= 0 && n_lead >= 0 && n_slot_col >= 0, "negative shape");
+    SCDRS_CHECK((n_lead == 0 || lead) && (n_slot_col == 0 || slots), "null pointer");
+    auto row_fn = [=](int64_t r, char* p) {
+        const float* row = lead + r * (int64_t)n_lead;
+        for (int j = 0; j < n_lead; ++j) {
+            *p++ = '\t';
+            p = fmt_f32(p, row[j]);
+        }
+        const uint8_t* s = slots + (size_t)r * n_slot_col * 16;
+        for (int j = 0; j < n_slot_col; ++j, s += 16) {
+            *p++ = '\t';
+            memcpy(p, s, 16);             // the tail beyond the length is overwritten by the next field
+            p += s[15];
+        }
+        return p;
+    };
+    return write_blocks(path, header, n_row, names, name_off, (size_t)(n_lead + n_slot_col) * 17 + 32, row_fn, n_thread, level);
 }

@@ -426,6 +426,7 @@ def score_traits(
     sharded=False,
     shard=None,
     max_prefetch=None,
+    text_output=False,
 ):
     """Score every gene set of ``dict_gs`` = {trait: (gene_list, gene_weight_list)}.
 
@@ -446,6 +447,12 @@ def score_traits(
     ``max_prefetch`` traits ahead, while the GPU scores the current one; result frames are built and handed to
     ``on_result(trait, df)`` (in ``.gs`` order) off the critical path.  Returns {trait: DataFrame}, or the list of
     scored traits when a callback is given.
+
+    ``text_output=True`` (needs ``on_result`` and ``return_ctrl_norm_score``; one GPU per process): the
+    ``ctrl_norm_score_*`` columns do not come back as floats.  The GPU turns them into the text of the score file
+    (``csrc/score_format.cu``) and the frame handed to ``on_result`` holds the six leading columns, with
+    ``df.attrs["ctrl_norm_text"]`` (uint8 ``[n_cell, n_ctrl, 16]`` text slots in pinned memory, valid until
+    ``on_result`` returns) and ``df.attrs["ctrl_norm_columns"]`` for ``_native.write_score_gz_slots``.
     """
     import os
     import time
@@ -473,6 +480,10 @@ def score_traits(
     state = get_state(adata)
     use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))
     mode, world, rank, n_tg, my_tg, cell_group = _shard_layout(sharded, shard)
+    text_output = bool(text_output and return_ctrl_norm_score and n_ctrl > 0)
+    if text_output:
+        assert on_result is not None, "text_output hands pinned text to on_result; it needs the callback"
+        assert mode != "cells", "text_output is a single-GPU path (score files of sharded runs are written per rank from floats)"
     all_traits = [t for t in dict_gs if len(dict_gs[t][0]) >= min_genes]
     traits = all_traits[my_tg::n_tg] if n_tg > 1 else all_traits
     if not traits and mode != "cells":
@@ -516,7 +527,9 @@ def score_traits(
         mark("matrix resident")
         state.ensure_cov(adata, implicit)
         ctx.set_gene_stats(tab.var, tab.var_tech)
+        ctx.set_text_output(text_output)
         mark("cov+stats resident")
+        text_writes = {}      # trait number -> future of the writer that still reads the trait's pinned text
         if cell_sharded:
             from .distributed import CudaPhases, DrawBroadcaster, ShardedScorer
 
@@ -529,9 +542,19 @@ def score_traits(
         written = []          # futures of on_result calls (one writer thread: .gs order is kept)
         in_flight = None      # (trait, ticket) submitted to the GPU and not collected yet
 
-        def collect(item):
+        def collect(item, i_prev=None):
             t_prev, ticket = item
             out_prev = scorer.collect(ticket) if cell_sharded else ctx.score_trait_collect(ticket)
+            if text_output:
+                # the six leading columns are cheap: build the frame here and hand it, with the pinned text of the
+                # control columns, straight to the writer thread; the slot is taken again two submits from now
+                df_prev = _result_frame(adata, out_prev, n_ctrl, return_ctrl_raw_score, False)
+                df_prev.attrs["ctrl_norm_text"] = out_prev["ctrl_norm_text"]
+                df_prev.attrs["ctrl_norm_columns"] = ["ctrl_norm_score_%d" % i for i in range(n_ctrl)]
+                fut = writer.submit(on_result, t_prev, df_prev)
+                text_writes[i_prev] = fut
+                written.append(fut)
+                return
             pending.append((t_prev, frame_pool.submit(_result_frame, adata, out_prev, n_ctrl, return_ctrl_raw_score,
                                                       return_ctrl_norm_score)))
             drain(2)
@@ -566,18 +589,20 @@ def score_traits(
                 else:
                     # the next trait is queued behind the current one before the current one's results are
                     # fetched: the GPU never waits for the host between traits
+                    if text_output and (i_t - 2) in text_writes:
+                        text_writes.pop(i_t - 2).result()      # this submit overwrites that trait's pinned text
                     ticket = ctx.score_trait_submit(prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"],
                                                     prep["ctrl_gw"], weight_opt, use_ratio,
                                                     want_ctrl_raw=return_ctrl_raw_score,
                                                     want_ctrl_norm=return_ctrl_norm_score)
                 mark("submitted %d" % i_t)
                 if in_flight is not None:
-                    collect(in_flight)
+                    collect(in_flight, i_t - 1)
                     mark("collected %d" % (i_t - 1))
                 in_flight = (t, ticket)
             if in_flight is not None:
                 last, in_flight = in_flight, None
-                collect(last)
+                collect(last, len(traits) - 1)
             drain(0)
             for w_ in written:
                 w_.result()
@@ -590,6 +615,12 @@ def score_traits(
                     ctx.score_trait_collect(in_flight[1])
                 except Exception:
                     pass
+            for w_ in written:              # nobody may still read pinned text when the context moves on
+                try:
+                    w_.result()
+                except Exception:
+                    pass
+            ctx.set_text_output(False)
     mark("done")
     if trace is not None:
         import sys

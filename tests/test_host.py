@@ -527,3 +527,48 @@ def test_h5ad_writer_round_trips_through_the_reader(tmp_path):
         assert np.array_equal(b.obs["n_genes"].values, a.obs["n_genes"].values)
         assert np.array_equal(b.obs["score"].values, a.obs["score"].values)
         assert np.array_equal(b.var["flag"].values.astype(bool), a.var["flag"].values)
+
+
+def test_device_formatter_function_against_to_chars(native_lib):
+    """fmt_f32_shortest -- the __host__ __device__ function the GPU formats score files with -- against the
+    std::to_chars writer over a stride of float32 bit patterns plus the boundaries of the positional range, and
+    the slot writer against the float writer on the same values.  (All 2^32 patterns: scdrs_selftest_format(0,
+    2**32, ...) -- 40 s on 8 threads, 0 mismatches; run by hand.)"""
+    import gzip
+
+    bad = ctypes.c_uint32()
+    L = _native.lib()
+    for first in range(0, 2 ** 32, 2 ** 27):
+        assert L.scdrs_selftest_format(first, 2 ** 17, 4, ctypes.byref(bad)) == 0, hex(bad.value)
+    for v in [1e-4, 9.9999997e-05, 1e6, 999999.94, 0.0, -0.0, 1e-45, 3.4028235e38, -1.5, 123456.0, np.inf, -np.inf]:
+        buf = ctypes.create_string_buffer(64)
+        n = L.scdrs_format_f32_shortest(ctypes.c_float(v), buf)
+        assert buf.raw[:n].decode() == _native.format_f32(v), v
+    buf = ctypes.create_string_buffer(64)
+    assert L.scdrs_format_f32_shortest(ctypes.c_float(np.nan), buf) == 0
+
+
+def test_slot_writer_equals_float_writer(native_lib, tmp_path):
+    import gzip
+
+    rng = np.random.default_rng(2)
+    n, n_lead, n_slot = 700, 6, 37
+    lead = rng.normal(size=(n, n_lead)).astype(np.float32)
+    tail = (rng.normal(size=(n, n_slot)) * 10.0 ** rng.integers(-7, 8, size=(n, n_slot))).astype(np.float32)
+    tail[3, 5] = np.nan
+    tail[4, 0] = 0.0
+    tail[5, 1], tail[5, 2] = -0.000123456784, -1.23456789e-10        # the longest texts: 15 characters
+    slots = np.zeros((n, n_slot, 16), dtype=np.uint8)
+    for i in range(n):
+        for j in range(n_slot):
+            txt = _native.format_f32(tail[i, j]).encode()
+            slots[i, j, :len(txt)] = np.frombuffer(txt, dtype=np.uint8)
+            slots[i, j, 15] = len(txt)
+    idx = ["c%d" % i for i in range(n)]
+    cols = ["l%d" % j for j in range(n_lead)]
+    extra = ["t%d" % j for j in range(n_slot)]
+    df_lead = pd.DataFrame(lead, index=idx, columns=cols)
+    df_full = pd.DataFrame(np.concatenate([lead, tail], axis=1), index=idx, columns=cols + extra)
+    _native.write_score_gz_slots(str(tmp_path / "a.gz"), df_lead, extra, slots, n_thread=3)
+    _native.write_score_gz(str(tmp_path / "b.gz"), df_full, n_thread=3)
+    assert gzip.open(str(tmp_path / "a.gz")).read() == gzip.open(str(tmp_path / "b.gz")).read()
