@@ -276,6 +276,8 @@ int scdrs_format_f32(float v, char* out64);
  * self-test against scdrs_format_f32 over the float32 bit patterns [first, first + count) (returns the number of
  * mismatches; the whole 2^32 range takes about a minute on 32 threads). */
 int scdrs_format_f32_shortest(float v, char* out64);
+/* Host restatement of the device formatting kernel: slots[n_val x 16] from vals[n_val] (tests, timing probes). */
+int scdrs_format_slots_host(int64_t n_val, const float* vals, uint8_t* slots, int32_t n_thread);
 int64_t scdrs_selftest_format(uint32_t first, uint64_t count, int32_t n_thread, uint32_t* bad_bits);
 
 #ifdef __cplusplus

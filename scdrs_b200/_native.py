@@ -90,6 +90,7 @@ SIGNATURES = {
     "scdrs_slot_text": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "scdrs_format_f32": (C.c_int, [C.c_float, C.c_char_p]),
     "scdrs_format_f32_shortest": (C.c_int, [C.c_float, C.c_char_p]),
+    "scdrs_format_slots_host": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "scdrs_selftest_format": (C.c_int64, [C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32)]),
 }
 

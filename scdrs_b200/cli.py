@@ -177,8 +177,9 @@ def compute_score(h5ad_file, h5ad_species, gs_file, gs_species, out_folder, cov_
             # the control columns were formatted on the GPU (csrc/score_format.cu): only copied and deflated here
             from scdrs_b200 import _native
 
+            text = df_res.attrs["ctrl_norm_text"]
             _native.write_score_gz_slots(os.path.join(out_folder, "%s.full_score.gz" % trait), df_res,
-                                         df_res.attrs["ctrl_norm_columns"], df_res.attrs["ctrl_norm_text"])
+                                         text.columns, text.array)
         elif flag_return_ctrl_raw_score | flag_return_ctrl_norm_score:
             util.write_score_file(os.path.join(out_folder, "%s.full_score.gz" % trait), df_res)
         v_fdr = util.fdr_bh(df_res["pval"].values)

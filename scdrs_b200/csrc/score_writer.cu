@@ -10,11 +10,13 @@
 // as independent gzip members and written in order; any gzip reader concatenates the members.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
 
 #include <atomic>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <string>
 #include <thread>
@@ -98,6 +100,23 @@ extern "C" int64_t scdrs_selftest_format(uint32_t first, uint64_t count, int32_t
     return bad.load();
 }
 
+// host restatement of format_slots_kernel (score_format.cu): what the GPU writes, for tests and timing probes
+extern "C" int scdrs_format_slots_host(int64_t n_val, const float* vals, uint8_t* slots, int32_t n_thread) {
+    SCDRS_CHECK(n_val >= 0 && (n_val == 0 || (vals && slots)), "null pointer");
+    if (n_thread < 1) n_thread = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thread; ++t)
+        pool.emplace_back([=]() {
+            for (int64_t i = t; i < n_val; i += n_thread) {
+                char c[16] = {0};
+                c[15] = (char)scdrs::fmt_f32_shortest(vals[i], c);
+                memcpy(slots + i * 16, c, 16);
+            }
+        });
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
 extern "C" int scdrs_format_f32_shortest(float v, char* out64) {
     const int n = scdrs::fmt_f32_shortest(v, out64);
     out64[n] = 0;
@@ -121,11 +140,16 @@ int write_blocks(const char* path, const char* header, int64_t n_row, const char
     std::vector<Block> blocks((size_t)n_block + 1);
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
+    const char* tr_env = getenv("SCDRS_B200_TRACE");
+    const bool trace = tr_env != nullptr && tr_env[0] == '1';
+    std::atomic<long long> ns_fmt{0}, ns_gz{0};
+    const auto t_begin = std::chrono::steady_clock::now();
     auto work = [&]() {
         std::vector<char> text;          // one buffer per thread, written through a raw pointer
         for (;;) {
             const int64_t b = next.fetch_add(1);
             if (b > n_block) return;
+            const auto t0 = std::chrono::steady_clock::now();
             size_t n_text = 0;
             if (b == 0) {
                 n_text = strlen(header);
@@ -144,8 +168,14 @@ int write_blocks(const char* path, const char* header, int64_t n_row, const char
                 }
                 n_text = (size_t)(p - text.data());
             }
+            const auto t1 = std::chrono::steady_clock::now();
             if (!deflate_member(text.data(), n_text, level, blocks[(size_t)b].gz)) failed.store(1);
             blocks[(size_t)b].ready.store(1, std::memory_order_release);
+            if (trace) {
+                const auto t2 = std::chrono::steady_clock::now();
+                ns_fmt += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+                ns_gz += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
+            }
         }
     };
     std::vector<std::thread> pool;
@@ -159,6 +189,10 @@ int write_blocks(const char* path, const char* header, int64_t n_row, const char
     }
     for (auto& t : pool) t.join();
     ok = (fclose(fh) == 0) && ok && !failed.load();
+    if (trace)
+        fprintf(stderr, "score writer %s: %.3f s wall, %d threads, thread-seconds: text %.2f, deflate %.2f\n", path,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), n_thread,
+                ns_fmt.load() * 1e-9, ns_gz.load() * 1e-9);
     SCDRS_CHECK(ok, "writing %s failed", path);
     return 0;
 }

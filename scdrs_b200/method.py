@@ -357,6 +357,21 @@ def _scratch_context():
 # ----------------------------------------------------------------------------------------------
 # many traits against one data set (what `scdrs compute-score` loops over, bin/scdrs:255-274)
 # ----------------------------------------------------------------------------------------------
+class DeviceText:
+    """The control columns of one trait as text slots in pinned memory (``score_traits(text_output=True)``).  pandas
+    deep-copies ``DataFrame.attrs`` whenever a frame is sliced; this handle copies as itself, so the 1.8 GB block
+    behind it is never duplicated.  ``array``: uint8 [n_cell, n_ctrl, 16]; ``columns``: the column names."""
+
+    def __init__(self, array, columns):
+        self.array, self.columns = array, columns
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+
 def _shard_layout(sharded, shard):
     """(mode, world, rank, n_trait_group, trait_group, cell_group) of this process.
 
@@ -451,8 +466,8 @@ def score_traits(
     ``text_output=True`` (needs ``on_result`` and ``return_ctrl_norm_score``; one GPU per process): the
     ``ctrl_norm_score_*`` columns do not come back as floats.  The GPU turns them into the text of the score file
     (``csrc/score_format.cu``) and the frame handed to ``on_result`` holds the six leading columns, with
-    ``df.attrs["ctrl_norm_text"]`` (uint8 ``[n_cell, n_ctrl, 16]`` text slots in pinned memory, valid until
-    ``on_result`` returns) and ``df.attrs["ctrl_norm_columns"]`` for ``_native.write_score_gz_slots``.
+    ``df.attrs["ctrl_norm_text"]`` = a ``DeviceText`` (``.array``: uint8 ``[n_cell, n_ctrl, 16]`` text slots in
+    pinned memory, valid until ``on_result`` returns; ``.columns``) for ``_native.write_score_gz_slots``.
     """
     import os
     import time
@@ -549,8 +564,8 @@ def score_traits(
                 # the six leading columns are cheap: build the frame here and hand it, with the pinned text of the
                 # control columns, straight to the writer thread; the slot is taken again two submits from now
                 df_prev = _result_frame(adata, out_prev, n_ctrl, return_ctrl_raw_score, False)
-                df_prev.attrs["ctrl_norm_text"] = out_prev["ctrl_norm_text"]
-                df_prev.attrs["ctrl_norm_columns"] = ["ctrl_norm_score_%d" % i for i in range(n_ctrl)]
+                df_prev.attrs["ctrl_norm_text"] = DeviceText(out_prev["ctrl_norm_text"],
+                                                             ["ctrl_norm_score_%d" % i for i in range(n_ctrl)])
                 fut = writer.submit(on_result, t_prev, df_prev)
                 text_writes[i_prev] = fut
                 written.append(fut)

@@ -82,9 +82,18 @@ def main():
         "h5ad_bytes": os.path.getsize(h5ad), "bytes_written": int(sum(os.path.getsize(f) for f in files)),
         "n_files": len(files),
     }
+    if os.environ.get("SCDRS_B200_TRACE", "0") == "1":
+        sys.stderr.write(r.stderr[-6000:])
     if m:
         res.update(load_s=float(m.group(1)), preprocess_s=float(m.group(2)), score_write_s=float(m.group(3)),
                    s_per_trait=float(m.group(4)), writer_s_per_trait=float(m.group(6)), cli_total_s=float(m.group(7)))
+    # steady state: differences of the per-trait "sys_time" stamps of the CLI's own log (the first traits carry the
+    # one-time allocations of pinned staging memory)
+    stamps = [float(x) for x in re.findall(r"^Trait=.*sys_time=([\d.]+)s\)", r.stdout, flags=re.M)]
+    if len(stamps) >= 4:
+        d = sorted(b - a_ for a_, b in zip(stamps[:-1], stamps[1:]))
+        res["s_per_trait_median_of_deltas"] = round(d[len(d) // 2], 3)
+        res["s_per_trait_deltas"] = [round(b - a_, 3) for a_, b in zip(stamps[:-1], stamps[1:])]
     # the files are what pandas reads back: spot-check one
     one = pd.read_csv(os.path.join(outd, "trait_00.full_score.gz"), sep="\t", index_col=0, nrows=5)
     res["full_score_columns"] = int(one.shape[1])
