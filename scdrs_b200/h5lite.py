@@ -68,7 +68,7 @@ class Dataset:
             addr = self._layout[1]
             if addr == UNDEF:
                 return b"\0" * nbytes
-            return f.buf[addr : addr + nbytes]
+            return f._view[addr : addr + nbytes]
         # chunked
         _, btree, cdims = self._layout
         esize = cdims[-1]
@@ -123,8 +123,12 @@ class Group:
 
 class File(Group):
     def __init__(self, path):
+        # the file is mapped, not read: dataset payloads are handed to numpy as views of the map and copied once
+        import mmap
+
         with open(path, "rb") as fh:
-            self.buf = fh.read()
+            self.buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        self._view = memoryview(self.buf)
         b = self.buf
         if b[:8] != b"\x89HDF\r\n\x1a\n":
             raise H5Error("%s is not an HDF5 file" % path)
@@ -233,7 +237,7 @@ class File(Group):
                 for i in range(n):
                     noff, ohdr = struct.unpack_from("<QQ", b, node + 8 + 40 * i)
                     s = dseg + noff
-                    links[b[s : b.index(b"\0", s)].decode()] = ohdr
+                    links[b[s : b.find(b"\0", s)].decode()] = ohdr
             else:
                 raise H5Error("bad group node")
 
