@@ -511,6 +511,7 @@ def main():
         p["d_ctrl"] = torch.from_numpy(np.ascontiguousarray(p["ctrl_cols"], dtype=np.int32)).to(device)
     # kernels run on torch's current stream (CudaPhases binds it) so that torch CUDA events bracket them
     scorer = ShardedScorer(CudaPhases(ctx, device), device, group=None if cell_sharded else False)
+    ctx.set_resident_sets(True)       # the control sets of this leg sit in HBM before the first step starts
 
     def barrier():
         torch.cuda.synchronize()
@@ -557,6 +558,7 @@ def main():
     work_cells = n_total                      # cells x traits scored by the whole job per step
     value = work_cells * len(names) * args.steps / wall
 
+    ctx.set_resident_sets(False)
     # ---- roofline of the dominant kernel: its own CUDA events (ctx.ev[0..1] around the scatter), one more pass
     step("spmm")
     barrier()

@@ -144,6 +144,13 @@ int scdrs_score_trait_collect(scdrs_ctx* ctx, int32_t slot, double* raw_score, f
  * block [n_cell x n_ctrl x 16] of its slot; it stays valid until the next submit that takes this slot (the one
  * after next).  The float matrix is then not available from scdrs_score_trait_collect (pass ctrl_norm = NULL). */
 int scdrs_ctx_set_text_output(scdrs_ctx* ctx, int32_t on);
+/* The list building of a trait runs on a second stream of the context, concurrently with the normalisation and
+ * null counting of the trait before it (it starts when that trait's raw-score scatter has finished).  Control sets
+ * handed over in DEVICE memory (scdrs_trait_raw_dev) are by default assumed to be produced on the context's stream
+ * right before the call (the receive buffer of a broadcast), which orders the preparation behind everything
+ * enqueued so far; a caller whose device-side control sets were complete before the previous trait was submitted
+ * (sets resident for the whole run) says so with on = 1 and gets the overlap there too. */
+int scdrs_ctx_set_resident_sets(scdrs_ctx* ctx, int32_t on);
 int scdrs_slot_text(scdrs_ctx* ctx, int32_t slot, const void** text, int64_t* n_bytes);
 
 /* The same split for the phase-by-phase (multi-GPU) driver: phase 1 with the control sets already in

@@ -87,6 +87,7 @@ SIGNATURES = {
     "scdrs_write_score_gz_slots": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                              C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "scdrs_ctx_set_text_output": (C.c_int, [C.c_void_p, C.c_int32]),
+    "scdrs_ctx_set_resident_sets": (C.c_int, [C.c_void_p, C.c_int32]),
     "scdrs_slot_text": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "scdrs_format_f32": (C.c_int, [C.c_float, C.c_char_p]),
     "scdrs_format_f32_shortest": (C.c_int, [C.c_float, C.c_char_p]),
@@ -278,6 +279,11 @@ class Context:
         """Traits submitted with want_ctrl_norm leave the device as text slots (scdrs_ctx_set_text_output)."""
         check(self._L.scdrs_ctx_set_text_output(self._h, int(bool(on))))
         self.text_output = bool(on)
+
+    def set_resident_sets(self, on):
+        """Device-side control sets given to trait_raw_dev were complete before the previous trait was submitted
+        (scdrs_ctx_set_resident_sets): their list building may overlap with that trait's tail."""
+        check(self._L.scdrs_ctx_set_resident_sets(self._h, int(bool(on))))
 
     def slot_text(self, slot, n_ctrl):
         """uint8 view [n_cell, n_ctrl, 16] of the pinned text block of a collected slot (valid until the submit after next)."""

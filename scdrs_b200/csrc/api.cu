@@ -138,7 +138,8 @@ static void release_all(scdrs_ctx* c) {
                       &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
-                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr,
+                      &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr, &c->ratio_a_alt, &c->colsum_alg_alt,
+                      &c->rnum, &c->stage_prep, &c->scan_tmp_prep,
                       &c->fx_xq, &c->fx_meta32, &c->text_slots, &c->ds_S, &c->ds_tmp, &c->ds_pos, &c->ds_M, &c->ds_keys,
                       &c->ds_vals, &c->ds_off, &c->ds_ref, &c->ds_chunk, &c->ds_part};
     for (DevBuf* b : bufs) b->release();
@@ -172,7 +173,13 @@ struct StageTrace {
 };
 }  // namespace
 
+// every API call but the scoring family may change what a trait preparation reads (matrix, gene statistics,
+// covariates, lists): the next preparation then orders itself behind the whole main stream
 #define CTX_GUARD(c)                                                       \
+    SCDRS_CHECK((c) != nullptr, "null context");                           \
+    SCDRS_CUDA(cudaSetDevice((c)->device));                                \
+    (c)->inputs_dirty = true
+#define CTX_GUARD_SCORING(c)                                               \
     SCDRS_CHECK((c) != nullptr, "null context");                           \
     SCDRS_CUDA(cudaSetDevice((c)->device))
 
@@ -235,6 +242,16 @@ int scdrs_ctx_create(int device, scdrs_ctx** out) {
     c->own_stream = true;
     for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
     c->timed_spmm = c->timed_trait = true;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        bool ok = cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->ev_scatter, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->ev_prep, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming) == cudaSuccess;
+        const char* e = getenv("SCDRS_B200_PREP_OVERLAP");
+        c->prep_overlap = ok && !(e != nullptr && e[0] == '0');
+    }
     *out = c;
     return 0;
 }
@@ -252,6 +269,9 @@ int scdrs_ctx_destroy(scdrs_ctx* c) {
     }
     for (int i = 0; i < 4; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->prep_stream) { cudaStreamSynchronize(c->prep_stream); cudaStreamDestroy(c->prep_stream); }
+    for (cudaEvent_t e : {c->ev_scatter, c->ev_prep, c->ev_mark})
+        if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -283,14 +303,14 @@ int scdrs_ctx_set_spmm_mode(scdrs_ctx* c, int32_t mode) {
 }
 
 int scdrs_ctx_last_spmm_kind(scdrs_ctx* c, int32_t* fixed_point, int32_t* scale_log2) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     if (fixed_point) *fixed_point = c->w_fx ? 1 : 0;
     if (scale_log2) *scale_log2 = c->w_fx ? c->fx_shift : 0;
     return 0;
 }
 
 int scdrs_ctx_last_timing(scdrs_ctx* c, float* spmm_ms, float* trait_ms) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
     if (spmm_ms) {
         *spmm_ms = -1.f;
@@ -432,7 +452,7 @@ int scdrs_trait_raw(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                     const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
                     const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
                     double* dev_colsum_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(trait_genes && trait_gw && (n_ctrl == 0 || n_s_ctrl == 0 || (ctrl_genes && ctrl_gw)), "null gene-set arrays");
     SCDRS_CHECK(dev_colsum_out != nullptr, "null output");
     SCDRS_TRY(trait_prepare(c, n_ctrl, n_s, n_s_ctrl, trait_genes, trait_gw, ctrl_genes, ctrl_gw,
@@ -443,14 +463,14 @@ int scdrs_trait_raw(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
 
 int scdrs_trait_rowstats(scdrs_ctx* c, const double* dev_colsum, int64_t n_cell_total,
                          double* dev_colsum2_out, double* dev_colmin_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(dev_colsum && dev_colsum2_out && dev_colmin_out, "null pointer");
     return bg_rowstats(c, dev_colsum, n_cell_total, dev_colsum2_out, dev_colmin_out);
 }
 
 int scdrs_trait_queries(scdrs_ctx* c, const double* dev_colsum2, const double* dev_colmin,
                         float* dev_query_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(dev_colsum2 && dev_colmin, "null pointer");
     SCDRS_TRY(c->query.reserve((size_t)c->n_cell * sizeof(float)));
     SCDRS_TRY(bg_queries(c, dev_colsum2, dev_colmin, c->query.as<float>()));
@@ -469,7 +489,7 @@ static int trait_count_impl(scdrs_ctx* c, const float* dev_query_all, int64_t n_
 
 int scdrs_trait_count(scdrs_ctx* c, const float* dev_query_all, int64_t n_query_all,
                       unsigned long long* dev_hist_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(dev_query_all && dev_hist_out, "null pointer");
     // the normalised control matrix is always kept in the phase API (finish may ask for it)
     return trait_count_impl(c, dev_query_all, n_query_all, dev_hist_out, true);
@@ -479,7 +499,7 @@ int scdrs_trait_finish(scdrs_ctx* c, const unsigned long long* dev_hist_all, int
                        int64_t query_offset, int64_t n_null_total, double* raw_score,
                        float* norm_score, int32_t* mc_count, int64_t* ge_count, float* ctrl_raw,
                        float* ctrl_norm) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(dev_hist_all != nullptr, "null pointer");
     const int64_t n = c->n_cell;
     SCDRS_CHECK(query_offset >= 0 && query_offset + n <= n_query_all, "query_offset out of range");
@@ -511,7 +531,7 @@ int scdrs_score_trait(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctr
                       const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
                       double* raw_score, float* norm_score, int32_t* mc_count, int64_t* ge_count,
                       float* ctrl_raw, float* ctrl_norm) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     const int ncol = n_ctrl + 1;
     SCDRS_CHECK(ncol >= 1, "n_ctrl < 0");
     SCDRS_TRY(c->x_colsum.reserve(ncol * sizeof(double)));
@@ -583,7 +603,7 @@ int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t 
                              const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
                              const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio,
                              int32_t want_ctrl_raw, int32_t want_ctrl_norm, int32_t* slot_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(slot_out != nullptr && trait_genes && trait_gw && n_ctrl >= 0 && n_s >= 0 && n_s_ctrl >= 0, "null pointer");
     SCDRS_CHECK(n_ctrl == 0 || n_s_ctrl == 0 || (ctrl_genes && ctrl_gw), "null gene-set arrays");
     const int id = c->next_slot;
@@ -639,7 +659,7 @@ int scdrs_score_trait_submit(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t 
 
 int scdrs_score_trait_collect(scdrs_ctx* c, int32_t slot, double* raw_score, float* norm_score, int32_t* mc_count,
                               int64_t* ge_count, float* ctrl_raw, float* ctrl_norm) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
     scdrs_ctx::Slot& sl = c->slot[slot];
     SCDRS_CHECK(sl.busy, "nothing was submitted to this slot");
@@ -665,8 +685,14 @@ int scdrs_ctx_set_text_output(scdrs_ctx* c, int32_t on) {
     return 0;
 }
 
-int scdrs_slot_text(scdrs_ctx* c, int32_t slot, const void** text, int64_t* n_bytes) {
+int scdrs_ctx_set_resident_sets(scdrs_ctx* c, int32_t on) {
     CTX_GUARD(c);
+    c->resident_sets = on != 0;
+    return 0;
+}
+
+int scdrs_slot_text(scdrs_ctx* c, int32_t slot, const void** text, int64_t* n_bytes) {
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
     SCDRS_CHECK(text != nullptr && n_bytes != nullptr, "null pointer");
     scdrs_ctx::Slot& sl = c->slot[slot];
@@ -683,7 +709,7 @@ int scdrs_slot_text(scdrs_ctx* c, int32_t slot, const void** text, int64_t* n_by
 int scdrs_trait_raw_dev(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl, const int32_t* trait_genes,
                         const double* trait_gw, const int32_t* dev_ctrl_genes, const double* ctrl_gw,
                         int32_t weight_opt, int32_t use_var_ratio, double* dev_colsum_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(trait_genes && trait_gw && n_ctrl >= 0 && n_s >= 0 && n_s_ctrl >= 0, "null pointer");
     SCDRS_CHECK(n_ctrl == 0 || n_s_ctrl == 0 || (dev_ctrl_genes && ctrl_gw), "null gene-set arrays");
     SCDRS_CHECK(dev_colsum_out != nullptr, "null output");
@@ -706,7 +732,7 @@ int scdrs_trait_raw_dev(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_c
 int scdrs_trait_finish_submit(scdrs_ctx* c, const unsigned long long* dev_hist_all, int64_t n_query_all,
                               int64_t query_offset, int64_t n_null_total, int32_t want_ctrl_raw,
                               int32_t want_ctrl_norm, int32_t* slot_out) {
-    CTX_GUARD(c);
+    CTX_GUARD_SCORING(c);
     SCDRS_CHECK(slot_out != nullptr, "null pointer");
     const int id = c->next_slot;
     scdrs_ctx::Slot& sl = c->slot[id];

@@ -55,6 +55,17 @@ struct scdrs_ctx {
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_spmm = false, timed_trait = false;
+    // The list building of trait i + 1 (prep_sets ... fx_place, ~0.3 ms of small kernels) runs on a second stream
+    // while the main stream still normalises and counts trait i: it starts when the scatter of trait i has finished
+    // (ev_scatter) and the scatter of trait i + 1 waits for it (ev_prep).  Scratch that both sides use exists twice
+    // (swapped in by PrepScope, spmm_score.cu); what the tail of trait i reads and the preparation of trait i + 1
+    // writes (ratio_a, colsum_alg) alternates between two buffers.
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t ev_scatter = nullptr, ev_prep = nullptr, ev_mark = nullptr;
+    bool prep_overlap = true;        // SCDRS_B200_PREP_OVERLAP=0 turns it off
+    bool scatter_marked = false;     // ev_scatter has been recorded since the inputs last changed
+    bool inputs_dirty = true;        // an API call other than the scoring family ran since the last preparation
+    bool resident_sets = false;      // device-side control sets are complete long before they are handed over
 
     // resident expression matrix (CSR)
     int64_t n_cell = 0, nnz = 0;
@@ -105,6 +116,7 @@ struct scdrs_ctx {
     int32_t n_ctrl = 0, n_s = 0, n_sc = 0, ncol = 0, ld = 0;  // n_s: trait set size, n_sc: control set size
     bool trait_ready = false;
     scdrs::DevBuf set_genes, set_gw, set_w, covM, covm, ratio_a;  // ratio_a: 1/sqrt(var ratio)
+    scdrs::DevBuf ratio_a_alt, colsum_alg_alt, rnum, stage_prep, scan_tmp_prep;   // see prep_stream
     scdrs::DevBuf w_ptr, w_cursor, w_col, w_val;        // compact gene-major lists (build scratch)
     scdrs::DevBuf p_ptr, p_meta, p_col, p_val, colscale, gbase;  // padded / bank-dealt lists the scatter reads
     bool w_binary = false;

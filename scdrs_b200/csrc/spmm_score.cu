@@ -22,6 +22,8 @@
 // deviations from it, NaN marking exact zeros (the `raw == 0` rule, scdrs/method.py:522-523).
 #include <math.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace scdrs {
@@ -436,7 +438,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
     SCDRS_TRY(c->colscale.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->gbase.reserve((size_t)n_gene * sizeof(double)));
     SCDRS_TRY(c->ratio_a.reserve(ncol * sizeof(double)));
-    SCDRS_TRY(c->colmean.reserve(ncol * sizeof(double)));  // reused as rnum scratch here
+    SCDRS_TRY(c->rnum.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->w_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->w_cursor.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
     SCDRS_TRY(c->p_ptr.reserve((size_t)(n_gene + 1) * sizeof(uint32_t)));
@@ -458,7 +460,7 @@ static int build_w(scdrs_ctx* c, int weight_opt, int use_var_ratio, bool explici
         c->have_stats ? c->var.as<double>() : nullptr,
         c->have_stats ? c->var_tech.as<double>() : nullptr, c->gbase.as<double>());
     SCDRS_LAUNCH_CHECK(c);
-    double* rnum = c->colmean.as<double>();
+    double* rnum = c->rnum.as<double>();
     prep_sets_kernel<<<ncol, 256, 0, c->stream>>>(
         n_s, n_sc, ncol, c->k, binary ? 1 : 0, c->set_genes.as<int32_t>(), c->set_gw.as<double>(),
         explicit_w ? c->stage.as<double>() : nullptr, c->gbase.as<double>(),
@@ -533,9 +535,47 @@ static int set_shape(scdrs_ctx* c, int32_t ncol, int32_t n_s, int32_t n_sc) {
     return 0;
 }
 
+// Runs a trait preparation on the context's second stream (see scdrs_ctx::prep_stream): everything launched inside
+// the scope goes to that stream and uses that stream's scratch; ratio_a / colsum_alg switch to the buffers the
+// already enqueued tail of the previous trait does not read.  The preparation starts when the previous scatter has
+// finished -- or, when the inputs may have changed since or the control sets are produced on the main stream, behind
+// everything enqueued so far -- and the main stream continues behind it.
+namespace {
+struct PrepScope {
+    scdrs_ctx* c;
+    bool on;
+    int rc = 0;
+    PrepScope(scdrs_ctx* ctx, bool after_whole_stream) : c(ctx), on(ctx->prep_overlap && ctx->prep_stream != nullptr) {
+        std::swap(c->ratio_a, c->ratio_a_alt);
+        std::swap(c->colsum_alg, c->colsum_alg_alt);
+        if (!on) return;
+        cudaEvent_t after = c->ev_scatter;
+        if (after_whole_stream || c->inputs_dirty || !c->scatter_marked) {
+            after = c->ev_mark;
+            if (cudaEventRecord(after, c->stream) != cudaSuccess) rc = 1;
+        }
+        if (rc == 0 && cudaStreamWaitEvent(c->prep_stream, after, 0) != cudaSuccess) rc = 1;
+        c->inputs_dirty = false;
+        std::swap(c->stream, c->prep_stream);
+        std::swap(c->stage, c->stage_prep);
+        std::swap(c->scan_tmp, c->scan_tmp_prep);
+    }
+    ~PrepScope() {
+        if (!on) return;
+        std::swap(c->stream, c->prep_stream);
+        std::swap(c->stage, c->stage_prep);
+        std::swap(c->scan_tmp, c->scan_tmp_prep);
+        // the main stream continues behind the preparation (also after an error: nothing may overtake it)
+        if (cudaEventRecord(c->ev_prep, c->prep_stream) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->ev_prep, 0);
+    }
+};
+}  // namespace
+
 int trait_prepare(scdrs_ctx* c, int32_t n_ctrl, int32_t n_s, int32_t n_s_ctrl,
                   const int32_t* trait_genes, const double* trait_gw, const int32_t* ctrl_genes,
                   const double* ctrl_gw, int32_t weight_opt, int32_t use_var_ratio, bool ctrl_on_device) {
+    PrepScope scope(c, ctrl_on_device && !c->resident_sets);
+    SCDRS_CHECK(scope.rc == 0, "could not order the trait preparation behind the main stream");
     SCDRS_CHECK(n_ctrl >= 0, "n_ctrl < 0");
     SCDRS_CHECK(weight_opt >= 0 && weight_opt <= 2, "illegal weight_opt %d", weight_opt);
     SCDRS_CHECK(weight_opt == SCDRS_WEIGHT_UNIFORM || c->have_stats,
@@ -740,8 +780,19 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
     }
 }
 
+static int spmm_score_f64(scdrs_ctx* c);
+
 int spmm_score(scdrs_ctx* c) {
-    if (c->w_fx) return fx_spmm(c);
+    SCDRS_TRY(c->w_fx ? fx_spmm(c) : spmm_score_f64(c));
+    // the preparation of the next trait may overwrite the lists from here on (PrepScope)
+    if (c->ev_scatter != nullptr) {
+        SCDRS_CUDA(cudaEventRecord(c->ev_scatter, c->stream));
+        c->scatter_marked = true;
+    }
+    return 0;
+}
+
+static int spmm_score_f64(scdrs_ctx* c) {
     const int ncol = c->ncol;
     SCDRS_TRY(c->dev_mat.reserve((size_t)c->n_cell * c->ld * sizeof(float)));
     SCDRS_TRY(c->row_ref.reserve((size_t)c->n_cell * sizeof(double)));
