@@ -251,6 +251,14 @@ int scdrs_ctx_create(int device, scdrs_ctx** out) {
         ok = ok && cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming) == cudaSuccess;
         const char* e = getenv("SCDRS_B200_PREP_OVERLAP");
         c->prep_overlap = ok && !(e != nullptr && e[0] == '0');
+        e = getenv("SCDRS_B200_TIMELINE");
+        if (e != nullptr && e[0] == '1') {
+            c->tl.on = true;
+            for (int i = 0; i < 16; ++i) {
+                cudaEventCreate(&c->tl.prep0[i]); cudaEventCreate(&c->tl.prep1[i]);
+                cudaEventCreate(&c->tl.sc0[i]); cudaEventCreate(&c->tl.sc1[i]);
+            }
+        }
     }
     *out = c;
     return 0;
@@ -289,6 +297,15 @@ int scdrs_ctx_set_stream(scdrs_ctx* c, void* cuda_stream) {
 int scdrs_ctx_sync(scdrs_ctx* c) {
     CTX_GUARD(c);
     SCDRS_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->tl.on && c->tl.n >= 16 && c->prep_overlap) {
+        SCDRS_CUDA(cudaStreamSynchronize(c->prep_stream));
+        const int first = c->tl.n - 15;          // the oldest complete entry of the ring
+        auto at = [&](cudaEvent_t e) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tl.sc0[first & 15], e); return ms; };
+        for (int t = first; t < c->tl.n; ++t)
+            fprintf(stderr, "timeline trait %d: prep %.3f .. %.3f  scatter %.3f .. %.3f\n", t, at(c->tl.prep0[t & 15]),
+                    at(c->tl.prep1[t & 15]), at(c->tl.sc0[t & 15]), at(c->tl.sc1[t & 15]));
+        c->tl.n = 0;
+    }
     return 0;
 }
 

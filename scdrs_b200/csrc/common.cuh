@@ -65,6 +65,13 @@ struct scdrs_ctx {
     bool prep_overlap = true;        // SCDRS_B200_PREP_OVERLAP=0 turns it off
     bool scatter_marked = false;     // ev_scatter has been recorded since the inputs last changed
     bool inputs_dirty = true;        // an API call other than the scoring family ran since the last preparation
+    // SCDRS_B200_TIMELINE=1: events around the preparation and the scatter of the last 16 traits, printed (relative
+    // to the first) by scdrs_ctx_sync -- where the device spends the time between two scatters
+    struct Timeline {
+        bool on = false;
+        int n = 0;
+        cudaEvent_t prep0[16], prep1[16], sc0[16], sc1[16];
+    } tl;
     bool resident_sets = false;      // device-side control sets are complete long before they are handed over
 
     // resident expression matrix (CSR)

@@ -559,9 +559,11 @@ struct PrepScope {
         std::swap(c->stream, c->prep_stream);
         std::swap(c->stage, c->stage_prep);
         std::swap(c->scan_tmp, c->scan_tmp_prep);
+        if (c->tl.on) cudaEventRecord(c->tl.prep0[c->tl.n & 15], c->stream);
     }
     ~PrepScope() {
         if (!on) return;
+        if (c->tl.on) cudaEventRecord(c->tl.prep1[c->tl.n & 15], c->stream);
         std::swap(c->stream, c->prep_stream);
         std::swap(c->stage, c->stage_prep);
         std::swap(c->scan_tmp, c->scan_tmp_prep);
@@ -783,7 +785,12 @@ spmm_score_kernel(int64_t n_cell, int ncol, int ld, int acc_stride,
 static int spmm_score_f64(scdrs_ctx* c);
 
 int spmm_score(scdrs_ctx* c) {
+    if (c->tl.on) cudaEventRecord(c->tl.sc0[c->tl.n & 15], c->stream);
     SCDRS_TRY(c->w_fx ? fx_spmm(c) : spmm_score_f64(c));
+    if (c->tl.on) {
+        cudaEventRecord(c->tl.sc1[c->tl.n & 15], c->stream);
+        ++c->tl.n;
+    }
     // the preparation of the next trait may overwrite the lists from here on (PrepScope)
     if (c->ev_scatter != nullptr) {
         SCDRS_CUDA(cudaEventRecord(c->ev_scatter, c->stream));
