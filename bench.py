@@ -332,7 +332,7 @@ def reference_arm(args):
     The unmodified reference spends ~20 s per trait on fixed Python overhead (1001 pandas label look-ups per
     gene set, scdrs/method.py:172-183) whatever the number of cells, so K = 20 steps of it do not fit "a few
     minutes".  One step of it is always run and reported (``reference_check``); the K timed steps use it when they
-    fit the budget (SCDRS_BENCH_REF_BUDGET_S, default 330 s) and otherwise the numpy port, which is 3-7x FASTER
+    fit the budget (SCDRS_BENCH_REF_BUDGET_S, default 560 s of a driver slot of ~800 s) and otherwise the numpy port, which is 3-7x FASTER
     than the reference per core -- the driver's ratio against it is conservative."""
     import multiprocessing as mp
 
@@ -343,7 +343,7 @@ def reference_arm(args):
         return
     os.environ.setdefault("TQDM_DISABLE", "1")
     t_arm = time.time()
-    budget = float(os.environ.get("SCDRS_BENCH_REF_BUDGET_S", "330"))
+    budget = float(os.environ.get("SCDRS_BENCH_REF_BUDGET_S", "560"))
     n_proc = max(1, min(os.cpu_count() or 1, 32))
     steps = max(1, args.steps)
 

@@ -107,10 +107,11 @@ def score_cell(
     ``raw_score, norm_score, mc_pval, pval, nlog10_pval, zscore[, ctrl_raw_score_*][, ctrl_norm_score_*]``).
 
     Differences from the reference, all outside the numerical contract: ``adata.X`` is NOT
-    converted to CSC in place (:98-99); ``weight_opt="od"`` (benchmarking only, :352-355) and
-    ``save_intermediate`` text dumps are not part of the accelerated path and raise.  The global
+    converted to CSC in place (:98-99); ``weight_opt="od"`` (benchmarking only, :352-355) raises.  The global
     numpy generator is left exactly where the reference leaves it (re-seeded, :96 / :276, then
-    advanced by the control draws, :301).
+    advanced by the control draws, :301).  ``save_intermediate`` (a file-path prefix, :507-596) writes the reference's
+    ten ``.tsv.gz`` dumps of the background-correction stages: a debugging aid, derived on the host from the raw
+    scores the device produced (``_dump_intermediate``); the returned frame does not depend on it.
     """
     np.random.seed(random_seed)                                       # :96
     adata = data.copy() if copy else data
@@ -135,8 +136,6 @@ def score_cell(
     )
     if weight_opt == "od":
         raise NotImplementedError("weight_opt='od' (benchmarking-only overdispersion score) is outside the B200 hot path")
-    if save_intermediate is not None:
-        raise NotImplementedError("save_intermediate text dumps are not supported by the B200 path")
 
     if verbose:
         msg = "# scdrs.method.score_cell summary:"
@@ -165,9 +164,57 @@ def score_cell(
     use_ratio = (ctrl_match_key == "mean_var") and (weight_opt in ("uniform", "vs", "inv_std"))  # :187
     out = ctx.score_trait(
         prep["trait_cols"], prep["trait_gw"], prep["ctrl_cols"], prep["ctrl_gw"], weight_opt, use_ratio,
-        want_ctrl_raw=return_ctrl_raw_score, want_ctrl_norm=return_ctrl_norm_score,
+        want_ctrl_raw=return_ctrl_raw_score or save_intermediate is not None, want_ctrl_norm=return_ctrl_norm_score,
     )
+    if save_intermediate is not None:
+        ratio = _var_ratio_c2t(prep, weight_opt, n_ctrl) if use_ratio else np.ones(n_ctrl)
+        _dump_intermediate(save_intermediate, out["raw_score"], out["ctrl_raw"], ratio)
     return _result_frame(adata, out, n_ctrl, return_ctrl_raw_score, return_ctrl_norm_score)
+
+
+def _var_ratio_c2t(prep, weight_opt, n_ctrl):
+    """Ratio of the independent variance of every control score to that of the disease score (:186-195), on the
+    host, for the ``save_intermediate`` dumps only (the device computes its own in ``prep_sets_kernel``)."""
+    var = prep["var"]
+
+    def weights(cols, gw):
+        base = {"uniform": np.ones(len(cols)), "vs": 1 / np.sqrt(prep["var_tech"][cols] + 1e-2),
+                "inv_std": 1 / np.sqrt(var[cols] + 1e-2)}[weight_opt] * gw
+        return base / base.sum()
+
+    w_t = weights(prep["trait_cols"], prep["trait_gw"])
+    num = np.array([(var[prep["ctrl_cols"][i]] * weights(prep["ctrl_cols"][i], prep["ctrl_gw"]) ** 2).sum()
+                    for i in range(n_ctrl)])
+    return num / (var[prep["trait_cols"]] * w_t ** 2).sum()
+
+
+def _dump_intermediate(prefix, v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t):
+    """The reference's ``save_intermediate`` files (:507-596): ``<prefix>.raw_score<stage>.tsv.gz`` and
+    ``<prefix>.ctrl_raw_score<stage>.tsv.gz`` for the raw scores and the four stages of the background correction,
+    ``%.9e``, tab separated.  Host numpy in float64 -- a debugging side output, not the scoring path."""
+    v = np.asarray(v_raw_score, dtype=np.float64).copy()
+    m = np.asarray(mat_ctrl_raw_score, dtype=np.float64).copy()
+    zero_v, zero_m = v == 0, m == 0
+
+    def dump(stage):
+        for name, arr in (("raw_score", v), ("ctrl_raw_score", m)):
+            np.savetxt("%s.%s%s.tsv.gz" % (prefix, name, stage), arr, fmt="%.9e", delimiter="\t")
+
+    dump("")
+    v = v - v.mean()                                                    # first gene-set alignment
+    m = (m - m.mean(axis=0)) / np.sqrt(np.asarray(v_var_ratio_c2t, dtype=np.float64))
+    dump(".1st_gs_alignment")
+    mu, sd = m.mean(axis=1), m.std(axis=1)                              # cell-wise standardisation
+    v = (v - mu) / sd
+    m = ((m.T - mu) / sd).T
+    dump(".cellwise_standardization")
+    v = v - v.mean()                                                    # second gene-set alignment
+    m = m - m.mean(axis=0)
+    dump(".2nd_gs_alignment")
+    floor = min(v.min(), m.min()) if m.size else v.min()                # zero raw scores get the smallest value
+    v[zero_v] = floor - 1e-3
+    m[zero_m] = floor
+    dump(".final")
 
 
 class _GeneTable:
@@ -330,7 +377,7 @@ def _correct_background(v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t, save_i
     The device computes in float64 and stores float32, so results carry float32 resolution.
     """
     if save_intermediate is not None:
-        raise NotImplementedError("save_intermediate text dumps are not supported by the B200 path")
+        _dump_intermediate(save_intermediate, v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t)
     return _scratch_context().correct_background(v_raw_score, mat_ctrl_raw_score, v_var_ratio_c2t)
 
 

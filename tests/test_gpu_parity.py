@@ -971,3 +971,23 @@ def test_text_output_writes_the_same_score_files(native_lib, tmp_path):
                                 return_ctrl_norm_score=True)
     assert np.allclose(one.values, df.values.astype(np.float32), rtol=0, atol=0, equal_nan=True)
     scdrs_b200.clear_device_cache()
+
+
+@pytest.mark.gpu
+def test_score_cell_save_intermediate_against_the_reference_dumps(sc, tmp_path):
+    """score_cell(save_intermediate=prefix) writes the reference's ten stage files (scdrs/method.py:507-596) from the
+    device's raw scores; the returned frame is the one without the option."""
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "ref_intermediate_sparse_cov_vs.npz"))
+    adata, cov, case = helpers.load_case(os.path.join(here, "golden", "ref_case_sparse_cov_vs.npz"))
+    kw = dict(gene_weight=case["gene_weight"], ctrl_match_key=case["ctrl_match_key"], n_ctrl=case["n_ctrl"],
+              weight_opt=case["weight_opt"])
+    prefix = str(tmp_path / "dump")
+    df = sc.score_cell(adata, case["gene_list"], save_intermediate=prefix, **kw)
+    assert df.equals(sc.score_cell(adata, case["gene_list"], **kw)) and df.shape[1] == 6
+    for key in gold.files:
+        got = np.loadtxt("%s.%s.tsv.gz" % (prefix, key), delimiter="\t")
+        assert got.shape == gold[key].shape, key
+        assert np.allclose(got, gold[key], rtol=RTOL, atol=ATOL), key      # control raw scores pass through float32

@@ -572,3 +572,26 @@ def test_slot_writer_equals_float_writer(native_lib, tmp_path):
     _native.write_score_gz_slots(str(tmp_path / "a.gz"), df_lead, extra, slots, n_thread=3)
     _native.write_score_gz(str(tmp_path / "b.gz"), df_full, n_thread=3)
     assert gzip.open(str(tmp_path / "a.gz")).read() == gzip.open(str(tmp_path / "b.gz")).read()
+
+
+def test_save_intermediate_dumps_match_the_reference_files(tmp_path):
+    """`save_intermediate` (scdrs/method.py:507-596): the ten stage dumps, written from the reference's raw scores and
+    the host restatement of the variance ratio, against the files the unmodified reference wrote for the same case
+    (tests/golden/make_golden_intermediate.py)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "ref_intermediate_sparse_cov_vs.npz"))
+    adata, cov, case = helpers.load_case(os.path.join(here, "golden", "ref_case_sparse_cov_vs.npz"))
+    prep = method._prepare_trait(adata, None, case["gene_list"], case["gene_weight"], case["ctrl_match_key"],
+                                 case["n_ctrl"], 200, 0)
+    ratio = method._var_ratio_c2t(prep, case["weight_opt"], case["n_ctrl"])
+    _, internals = orc.score_cell(adata, case["gene_list"], gene_weight=case["gene_weight"],
+                                  ctrl_match_key=case["ctrl_match_key"], n_ctrl=case["n_ctrl"],
+                                  weight_opt=case["weight_opt"], return_internals=True)
+    assert np.allclose(ratio, internals["ratio"], rtol=1e-12)
+    prefix = str(tmp_path / "dump")
+    method._dump_intermediate(prefix, gold["raw_score"], gold["ctrl_raw_score"], ratio)
+    assert len(gold.files) == 10
+    for key in gold.files:
+        got = np.loadtxt("%s.%s.tsv.gz" % (prefix, key), delimiter="\t")
+        assert got.shape == gold[key].shape, key
+        assert np.allclose(got, gold[key], rtol=1e-6, atol=1e-7), key
