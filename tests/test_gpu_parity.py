@@ -991,3 +991,29 @@ def test_score_cell_save_intermediate_against_the_reference_dumps(sc, tmp_path):
         got = np.loadtxt("%s.%s.tsv.gz" % (prefix, key), delimiter="\t")
         assert got.shape == gold[key].shape, key
         assert np.allclose(got, gold[key], rtol=RTOL, atol=ATOL), key      # control raw scores pass through float32
+
+
+@pytest.mark.gpu
+def test_overlapped_trait_preparation_equals_the_serial_order(native_lib, monkeypatch):
+    """The list building of trait i + 1 runs on a second stream under the tail of trait i (scdrs_ctx::prep_stream).
+    Gene sets of very different sizes, binary and weighted, enough cells for the tails to take a while: every frame
+    must equal, bit for bit, the frame of a context that does everything on one stream, run after run."""
+    import scdrs_b200
+    from scdrs_b200 import synth
+    from scdrs_b200.loess1d import loess
+
+    adata, cov = synth.make_adata(20000, 5000, density=0.1, seed=77)
+    scdrs_b200.preprocess(adata, cov=cov)
+    traits = {}
+    for i, (n_g, weighted) in enumerate([(40, False), (900, False), (150, True), (1200, False), (60, True), (400, False),
+                                         (30, False), (700, True), (250, False), (1000, True), (80, False), (500, False)]):
+        g, w = synth.make_traits(adata.var_names, 1, n_g, weighted=weighted, seed=300 + i)["trait_00"]
+        traits["t%02d" % i] = (g, w)
+    runs = [scdrs_b200.score_traits(adata, traits, n_ctrl=400, return_ctrl_norm_score=True) for _ in range(2)]
+    monkeypatch.setenv("SCDRS_B200_PREP_OVERLAP", "0")
+    scdrs_b200.clear_device_cache()                       # the next context reads the switch
+    serial = scdrs_b200.score_traits(adata, traits, n_ctrl=400, return_ctrl_norm_score=True)
+    for t in traits:
+        for r in runs:
+            assert np.array_equal(r[t].values, serial[t].values, equal_nan=True), t
+    scdrs_b200.clear_device_cache()
