@@ -209,13 +209,120 @@ rowstats_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_
     }
 }
 
+
+// Same statistics for score matrices of at most 1 + 1024 columns (one pass of the fixed-point scatter), with ONE read of
+// the matrix: a CTA of 8 warps owns blocks of 16 rows (two CTAs per SM: one loads while the other sums columns); a warp loads a whole row (32 independent 128-byte loads per
+// lane in flight), keeps its aligned control scores in registers for the mean and the centred second moment, and
+// leaves the raw deviations in a shared-memory tile from which the per-column pass (a thread per column, rows in
+// order) reads them again -- rowstats_kernel above reads every value three times (once from DRAM, twice from L2).
+constexpr int kTileThreads = 256, kTileWarps = kTileThreads / 32, kTileMaxCtrl = 1024, kTileRows = 16, kTilePerSM = 2;
+
+__global__ void __launch_bounds__(kTileThreads, kTilePerSM)
+rowstats_tile_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_mat,
+                     const double* __restrict__ row_ref, const double* __restrict__ colmean,
+                     const double* __restrict__ ratio_a, double* __restrict__ row_mean,
+                     double* __restrict__ row_istd, double* __restrict__ part_sum,
+                     double* __restrict__ part_min) {
+    extern __shared__ double sh[];
+    double* sh_cm = sh;             // [ncol] column means of raw
+    double* sh_a = sh + ncol;       // [ncol] 1/sqrt(ratio)
+    double* sh_sum = sh + 2 * ncol; // [ncol] partial sums of n
+    double* sh_min = sh + 3 * ncol; // [ncol] partial minima of n
+    float* tile = reinterpret_cast<float*>(sh + 4 * ncol);      // [kTileRows][ncol] raw deviations
+    __shared__ double sh_ref[kTileRows], sh_mu[kTileRows], sh_is[kTileRows];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < ncol; j += kTileThreads) {
+        sh_cm[j] = colmean[j];
+        sh_a[j] = ratio_a[j];
+        sh_sum[j] = 0.0;
+        sh_min[j] = INFINITY;
+    }
+    const int n_ctrl = ncol - 1;
+    const int64_t nblk = (n_cell + kTileRows - 1) / kTileRows;
+    for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const int64_t r0 = b * kTileRows;
+        const int nr = (int)((n_cell - r0) < kTileRows ? (n_cell - r0) : kTileRows);
+        __syncthreads();
+        // phase 1: one warp per row; lane l owns the control columns 1 + l + 32 t
+        for (int r = warp; r < nr; r += kTileWarps) {
+            const int64_t row = r0 + r;
+            const double ref = row_ref[row];
+            const float* p = dev_mat + row * ld;
+            float* trow = tile + (size_t)r * ncol;
+            float d[kTileMaxCtrl / 32];
+#pragma unroll
+            for (int t = 0; t < kTileMaxCtrl / 32; ++t) {
+                const int j = 1 + lane + 32 * t;
+                d[t] = j < ncol ? __ldg(p + j) : 0.f;
+            }
+            if (lane == 0) trow[0] = __ldg(p);
+            double z[kTileMaxCtrl / 32];
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < kTileMaxCtrl / 32; ++t) {
+                const int j = 1 + lane + 32 * t;
+                if (j < ncol) {
+                    trow[j] = d[t];
+                    z[t] = aligned_value(ref, d[t], sh_cm[j], sh_a[j]);
+                    s += z[t];
+                } else {
+                    z[t] = 0.0;
+                }
+            }
+            s = warp_sum_d(s);
+            const double mu = n_ctrl > 0 ? s / (double)n_ctrl : 0.0;
+            double q = 0.0;
+#pragma unroll
+            for (int t = 0; t < kTileMaxCtrl / 32; ++t) {
+                const int j = 1 + lane + 32 * t;
+                if (j < ncol) {
+                    const double c = z[t] - mu;
+                    q = fma(c, c, q);
+                }
+            }
+            q = warp_sum_d(q);
+            const double sd = n_ctrl > 0 ? sqrt(q / (double)n_ctrl) : 0.0;
+            if (lane == 0) {
+                const double is = 1.0 / sd;
+                sh_ref[r] = ref;
+                sh_mu[r] = mu;
+                sh_is[r] = is;
+                row_mean[row] = mu;
+                row_istd[row] = is;
+            }
+        }
+        __syncthreads();
+        // phase 2: one thread per column, sums and minima of the standardised scores, rows in order
+        for (int j = threadIdx.x; j < ncol; j += kTileThreads) {
+            const double cm = sh_cm[j], a = sh_a[j];
+            double s = 0.0, mn = INFINITY;
+#pragma unroll 8
+            for (int r = 0; r < nr; ++r) {
+                const double zz = aligned_value(sh_ref[r], tile[(size_t)r * ncol + j], cm, a);
+                const double v = __dmul_rn(zz - sh_mu[r], sh_is[r]);
+                s += v;
+                mn = min_nan(mn, v);
+            }
+            sh_sum[j] += s;
+            sh_min[j] = min_nan(sh_min[j], mn);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncol; j += kTileThreads) {
+        part_sum[(size_t)blockIdx.x * ncol + j] = sh_sum[j];
+        part_min[(size_t)blockIdx.x * ncol + j] = sh_min[j];
+    }
+}
+
 int bg_rowstats(scdrs_ctx* c, const double* dev_colsum, int64_t n_cell_total, double* dev_col2,
                 double* dev_colmin) {
     SCDRS_CHECK(c->trait_ready, "no raw scores resident (call scdrs_trait_raw first)");
     SCDRS_CHECK(n_cell_total >= c->n_cell, "n_cell_total smaller than the local cell count");
     const int ncol = c->ncol;
     c->n_cell_total = n_cell_total;
-    const int g = grid_for(c->n_cell);
+    const bool tiled = ncol <= 1 + kTileMaxCtrl;
+    const int64_t nblk_rows = (c->n_cell + kTileRows - 1) / kTileRows, g_tile = (int64_t)kNumSM * kTilePerSM;
+    const int g = tiled ? (int)(nblk_rows < g_tile ? (nblk_rows < 1 ? 1 : nblk_rows) : g_tile) : grid_for(c->n_cell);
     SCDRS_TRY(c->partial.reserve((size_t)g * ncol * sizeof(double) * 2));
     SCDRS_TRY(c->colmean.reserve(ncol * sizeof(double)));
     SCDRS_TRY(c->row_mean.reserve((size_t)c->n_cell * sizeof(double)));
@@ -223,19 +330,28 @@ int bg_rowstats(scdrs_ctx* c, const double* dev_colsum, int64_t n_cell_total, do
     colmean_kernel<<<(ncol + 127) / 128, 128, 0, c->stream>>>(ncol, 1.0 / (double)n_cell_total,
                                                               dev_colsum, c->colmean.as<double>());
     SCDRS_LAUNCH_CHECK(c);
-    const size_t smem = (size_t)ncol * 4 * sizeof(double);
-    SCDRS_CHECK(smem <= 200 * 1024, "1 + n_ctrl too large for the row-statistics kernel");
+    double* psum = c->partial.as<double>();
+    double* pmin = psum + (size_t)g * ncol;
     static bool attr = false;
     if (!attr) {
         SCDRS_CUDA(cudaFuncSetAttribute(rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCDRS_CUDA(cudaFuncSetAttribute(rowstats_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    double* psum = c->partial.as<double>();
-    double* pmin = psum + (size_t)g * ncol;
-    rowstats_kernel<<<g, kThreads, smem, c->stream>>>(
-        c->n_cell, ncol, c->ld, c->dev_mat.as<float>(), c->row_ref.as<double>(),
-        c->colmean.as<double>(), c->ratio_a.as<double>(), c->row_mean.as<double>(),
-        c->row_istd.as<double>(), psum, pmin);
+    if (tiled) {
+        const size_t smem = (size_t)ncol * 4 * sizeof(double) + (size_t)kTileRows * ncol * sizeof(float);
+        rowstats_tile_kernel<<<g, kTileThreads, smem, c->stream>>>(
+            c->n_cell, ncol, c->ld, c->dev_mat.as<float>(), c->row_ref.as<double>(),
+            c->colmean.as<double>(), c->ratio_a.as<double>(), c->row_mean.as<double>(),
+            c->row_istd.as<double>(), psum, pmin);
+    } else {
+        const size_t smem = (size_t)ncol * 4 * sizeof(double);
+        SCDRS_CHECK(smem <= 200 * 1024, "1 + n_ctrl too large for the row-statistics kernel");
+        rowstats_kernel<<<g, kThreads, smem, c->stream>>>(
+            c->n_cell, ncol, c->ld, c->dev_mat.as<float>(), c->row_ref.as<double>(),
+            c->colmean.as<double>(), c->ratio_a.as<double>(), c->row_mean.as<double>(),
+            c->row_istd.as<double>(), psum, pmin);
+    }
     SCDRS_LAUNCH_CHECK(c);
     reduce_partials_kernel<<<(ncol + 31) / 32, kRedWarps * 32, 0, c->stream>>>(g, ncol, 0, psum, dev_col2);
     SCDRS_LAUNCH_CHECK(c);
