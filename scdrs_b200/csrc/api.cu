@@ -135,7 +135,7 @@ static void release_all(scdrs_ctx* c) {
                       &c->dev_mat, &c->row_ref, &c->partial, &c->colmean, &c->col2, &c->colmin,
                       &c->row_mean, &c->row_istd, &c->scalars, &c->query, &c->mc_count, &c->norm_mat,
                       &c->sort_keys[0], &c->sort_keys[1], &c->sort_idx[0], &c->sort_idx[1],
-                      &c->sort_tab, &c->grid, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
+                      &c->sort_tab, &c->grid, &c->grid_cells, &c->hist, &c->ge_sorted, &c->ge_local, &c->scan_tmp,
                       &c->x_colsum, &c->x_col2, &c->x_colmin, &c->x_hist, &c->stage,
                       &c->w_code, &c->w_rounds, &c->fx_part, &c->tile_ptr,
                       &c->gene_xsum, &c->cov_colsum, &c->colsum_alg, &c->fx_scal, &c->fx_rowctr, &c->ratio_a_alt, &c->colsum_alg_alt,

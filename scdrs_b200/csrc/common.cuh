@@ -149,7 +149,8 @@ struct scdrs_ctx {
     scdrs::DevBuf query, mc_count, norm_mat;
     int64_t n_cell_total = 0;
     // pooled-null workspace
-    scdrs::DevBuf sort_keys[2], sort_idx[2], sort_tab, grid, hist, ge_sorted, ge_local, scan_tmp;
+    scdrs::DevBuf sort_keys[2], sort_idx[2], sort_tab, grid, grid_cells, hist, ge_sorted, ge_local, scan_tmp;
+    bool cells_ready = false;   // grid_cells holds the 8-byte cell table of the current sorted queries
     int32_t grid_bits = 0;  // number of grid cells
     int sorted_buf = 0;     // which sort buffer holds the sorted queries
     // single-GPU exchange buffers

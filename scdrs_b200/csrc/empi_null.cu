@@ -17,6 +17,7 @@
 // Across GPUs the queries are all-gathered, every rank counts its own null values against all of
 // them and the histograms are summed (NCCL all-reduce): the pooled null never crosses NVLink.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace scdrs {
@@ -329,9 +330,53 @@ __device__ __forceinline__ uint32_t queries_le(F v, F lo, F scale, int n_cells,
     return a;
 }
 
+// Cell table of the pooled-null pass: 8 bytes per grid cell, ONE load answers almost every null value.
+//   .x = first sorted query of the cell | min(queries in the cell, 31) << 27      (m < 2^27)
+//   .y = key of that first query
+// no query in the cell -> position = first; one query -> first + (key <= value); more -> first when the value is
+// below the first query, else a search among the cell's queries (31: the cell ends where the next one starts).
+constexpr int kCellCntShift = 27;
+constexpr uint32_t kCellCntMax = 31u, kCellStartMask = (1u << kCellCntShift) - 1u;
+
+__global__ void grid_pack8_kernel(int n_cells, const uint32_t* __restrict__ grid, const uint32_t* __restrict__ keys,
+                                  uint2* __restrict__ cells) {
+    const int64_t cc = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cc > n_cells) return;
+    const uint32_t a = grid[cc];
+    uint32_t cnt = 0u, key0 = 0u;
+    if (cc < n_cells) {
+        cnt = grid[cc + 1] - a;
+        if (cnt > 0u) key0 = keys[a];
+        if (cnt > kCellCntMax) cnt = kCellCntMax;
+    }
+    cells[cc] = make_uint2(a | (cnt << kCellCntShift), key0);
+}
+
+// number of sorted queries <= v (float keys); same result as queries_le
+__device__ __forceinline__ uint32_t queries_le_cells(float v, float lo, float scale, int n_cells,
+                                                     const uint2* __restrict__ cells,
+                                                     const uint32_t* __restrict__ keys) {
+    const int cell = grid_cell<float>(v, lo, scale, n_cells);
+    const uint2 e = __ldg(cells + cell);
+    const uint32_t cnt = e.x >> kCellCntShift;
+    uint32_t a = e.x & kCellStartMask;
+    if (cnt == 0u) return a;
+    const uint32_t kv = KeyOf<float>::make(v);
+    if (kv < e.y) return a;
+    ++a;                                              // the first query of the cell is <= v
+    if (cnt == 1u) return a;
+    uint32_t b = cnt < kCellCntMax ? a + cnt - 1u : (__ldg(&cells[cell + 1].x) & kCellStartMask);
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (keys[mid] <= kv) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
 static int choose_grid_cells(int64_t m) {
+    // 8 - 16 cells per query (most cells then hold no query or one), at most 2^23 cells (64 MB of cell table)
     int64_t g = 1024;
-    while (g < 4 * m && g < (1 << 24)) g <<= 1;
+    while (g < 8 * m && g < (1 << 23)) g <<= 1;
     return (int)g;
 }
 
@@ -357,6 +402,15 @@ static int prepare_queries(scdrs_ctx* c, const F* dev_q, int64_t m, int* sorted_
     grid_build_kernel<F><<<(unsigned)((n_cells + 256) / 256), 256, 0, c->stream>>>(
         m, n_cells, c->sort_keys[*sorted_buf].as<K>(), params, c->grid.as<uint32_t>());
     SCDRS_LAUNCH_CHECK(c);
+    c->cells_ready = false;
+    if (sizeof(F) == 4 && m < ((int64_t)1 << kCellCntShift)) {
+        SCDRS_TRY(c->grid_cells.reserve(((size_t)n_cells + 1) * sizeof(uint2)));
+        grid_pack8_kernel<<<(unsigned)((n_cells + 256) / 256), 256, 0, c->stream>>>(
+            n_cells, c->grid.as<uint32_t>(), reinterpret_cast<const uint32_t*>(c->sort_keys[*sorted_buf].p),
+            c->grid_cells.as<uint2>());
+        SCDRS_LAUNCH_CHECK(c);
+        c->cells_ready = true;
+    }
     return 0;
 }
 
@@ -368,13 +422,15 @@ int null_prepare_queries(scdrs_ctx* c, const float* dev_query_all, int64_t m) {
 // One warp per cell.  Recomputes the final normalised control scores (second alignment and zero
 // rule, scdrs/method.py:565, :583), optionally stores them, counts controls >= trait (mc_pval) and
 // bumps the pooled-null histogram.
+template <bool CELLS>
 __global__ void __launch_bounds__(256)
 null_count_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ dev_mat,
                   const double* __restrict__ row_ref, const double* __restrict__ colmean,
                   const double* __restrict__ ratio_a, const double* __restrict__ row_mean,
                   const double* __restrict__ row_istd, const double* __restrict__ col2,
                   const double* __restrict__ scalars, const float* __restrict__ query_local,
-                  const uint32_t* __restrict__ grid, const uint32_t* __restrict__ qkeys, int n_cells,
+                  const uint32_t* __restrict__ grid, const uint2* __restrict__ cells,
+                  const uint32_t* __restrict__ qkeys, int n_cells,
                   unsigned long long* __restrict__ hist, int32_t* __restrict__ mc_count,
                   float* __restrict__ norm_mat) {
     const int lane = threadIdx.x & 31;
@@ -390,7 +446,7 @@ null_count_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ de
         const float* p = dev_mat + row * ld;
         int mc = 0;
         for (int j = 1 + lane; j < ncol; j += 32) {
-            const float d = p[j];
+            const float d = __ldcs(p + j);             // streamed once: the look-up tables should stay in L2
             float v;
             if (isnan(d)) {
                 v = gmin;
@@ -400,7 +456,8 @@ null_count_kernel(int64_t n_cell, int ncol, int ld, const float* __restrict__ de
             }
             if (norm_mat != nullptr) norm_mat[row * n_ctrl + (j - 1)] = v;
             mc += (v >= t) ? 1 : 0;
-            const uint32_t pos = queries_le<float>(v, lo, scale, n_cells, grid, qkeys);
+            const uint32_t pos = CELLS ? queries_le_cells(v, lo, scale, n_cells, cells, qkeys)
+                                       : queries_le<float>(v, lo, scale, n_cells, grid, qkeys);
             atomicAdd(&hist[pos], 1ull);
         }
 #pragma unroll
@@ -417,12 +474,14 @@ int null_count_pass(scdrs_ctx* c, unsigned long long* dev_hist, int64_t m, bool 
     int64_t grid = (c->n_cell + 7) / 8;
     if (grid > kNumSM * 8) grid = kNumSM * 8;
     if (grid < 1) grid = 1;
-    null_count_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(
+    // the 8-byte cell table when the queries fit its 27-bit positions, else the plain grid + search
+    auto kernel = c->cells_ready ? null_count_kernel<true> : null_count_kernel<false>;
+    kernel<<<(unsigned)grid, 256, 0, c->stream>>>(
         c->n_cell, c->ncol, c->ld, c->dev_mat.as<float>(), c->row_ref.as<double>(),
         c->colmean.as<double>(), c->ratio_a.as<double>(), c->row_mean.as<double>(),
         c->row_istd.as<double>(), c->col2.as<double>(), c->scalars.as<double>(),
-        c->query.as<float>(), c->grid.as<uint32_t>(), c->sort_keys[c->sorted_buf].as<uint32_t>(),
-        c->grid_bits, dev_hist, c->mc_count.as<int32_t>(),
+        c->query.as<float>(), c->grid.as<uint32_t>(), c->grid_cells.as<uint2>(),
+        c->sort_keys[c->sorted_buf].as<uint32_t>(), c->grid_bits, dev_hist, c->mc_count.as<int32_t>(),
         write_norm ? c->norm_mat.as<float>() : nullptr);
     SCDRS_LAUNCH_CHECK(c);
     return 0;
