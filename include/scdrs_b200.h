@@ -286,6 +286,9 @@ int scdrs_format_f32_shortest(float v, char* out64);
 /* Host restatement of the device formatting kernel: slots[n_val x 16] from vals[n_val] (tests, timing probes). */
 int scdrs_format_slots_host(int64_t n_val, const float* vals, uint8_t* slots, int32_t n_thread);
 int64_t scdrs_selftest_format(uint32_t first, uint64_t count, int32_t n_thread, uint32_t* bad_bits);
+/* One gzip member of `text` as the score-file writer produces it at `level` (1: the literal-only dynamic-Huffman
+ * encoder of score_writer.cu, 0 / 2..9: zlib) into out[0 .. cap); *out_len = bytes written.  For tests and timing. */
+int scdrs_gzip_member(const char* text, int64_t n_text, int32_t level, uint8_t* out, int64_t cap, int64_t* out_len);
 
 #ifdef __cplusplus
 }

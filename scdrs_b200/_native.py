@@ -93,6 +93,7 @@ SIGNATURES = {
     "scdrs_format_f32_shortest": (C.c_int, [C.c_float, C.c_char_p]),
     "scdrs_format_slots_host": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "scdrs_selftest_format": (C.c_int64, [C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32)]),
+    "scdrs_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 WEIGHT_OPT = {"uniform": 0, "vs": 1, "inv_std": 2}
@@ -568,6 +569,16 @@ def write_score_gz_slots(path, df_lead, extra_columns, slots, n_thread=None, lev
     check(lib().scdrs_write_score_gz_slots(os.fsencode(path), header.encode("utf-8"), values.shape[0],
                                            C.cast(buf, C.c_void_p), ptr(off), values.shape[1], ptr(values),
                                            slots.shape[1], slots.ctypes.data, int(n_thread), int(level)))
+
+
+def gzip_member(text, level=1):
+    """One gzip member as the score-file writer emits it (level 1: the literal-only Huffman encoder; else zlib)."""
+    text = bytes(text)
+    cap = len(text) + len(text) // 8 + 1024
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    check(lib().scdrs_gzip_member(text, len(text), int(level), out.ctypes.data, cap, C.byref(n)))
+    return out[: n.value].tobytes()
 
 
 def format_f32(v):

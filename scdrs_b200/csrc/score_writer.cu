@@ -20,6 +20,7 @@
 #include <cmath>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -51,7 +52,7 @@ struct Block {
     std::atomic<int> ready{0};
 };
 
-bool deflate_member(const char* text, size_t n_text, int level, std::string& out) {
+bool zlib_member(const char* text, size_t n_text, int level, std::string& out) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
@@ -66,7 +67,199 @@ bool deflate_member(const char* text, size_t n_text, int level, std::string& out
     return rc == Z_STREAM_END;
 }
 
+// ---- level 1: one literal-only dynamic-Huffman deflate block per gzip member --------------------------------
+// Score files are digits, '.', '-', 'e', tabs and cell names: LZ77 matches buy nothing (zlib level 1 reaches 0.48 of
+// the text, the order-0 entropy is 0.46) and cost almost all of zlib's time.  This writes RFC 1951 by hand: byte
+// histogram -> length-limited Huffman code -> block header -> one table look-up and a shift per byte.  Any gzip
+// reader accepts the members (BTYPE = 2, a single unused distance code).
+struct BitSink {
+    unsigned char* p;
+    uint64_t buf = 0;
+    int n = 0;
+    inline void put(uint32_t code, int len) {          // len <= 32 at a time; the buffer is drained below 32 bits
+        buf |= (uint64_t)code << n;
+        n += len;
+        if (n >= 32) {
+            memcpy(p, &buf, 4);                         // little endian
+            p += 4;
+            buf >>= 32;
+            n -= 32;
+        }
+    }
+    inline unsigned char* finish() {
+        while (n > 0) {
+            *p++ = (unsigned char)buf;
+            buf >>= 8;
+            n -= 8;
+        }
+        return p;
+    }
+};
+
+// code lengths (<= max_len) of a Huffman code for freq[0 .. n): plain Huffman; when the tree is too deep the
+// frequencies are flattened (halved, floor 1) and the tree rebuilt -- a few iterations at most, rarely any
+void huff_lengths(const uint64_t* freq, int n, int max_len, unsigned char* len) {
+    std::vector<uint64_t> f(freq, freq + n);
+    for (;;) {
+        struct Node { uint64_t w; int l, r; };
+        std::vector<Node> nodes;
+        std::vector<int> live;
+        for (int i = 0; i < n; ++i) {
+            len[i] = 0;
+            if (f[i] > 0) { nodes.push_back({f[i], -1 - i, -1}); live.push_back((int)nodes.size() - 1); }
+        }
+        if (live.empty()) return;
+        if (live.size() == 1) { len[-1 - nodes[(size_t)live[0]].l] = 1; return; }
+        while (live.size() > 1) {                    // the alphabet is tiny (<= 257): selection by scanning is fine
+            int a = 0, b = 1;
+            if (nodes[(size_t)live[(size_t)b]].w < nodes[(size_t)live[(size_t)a]].w) std::swap(a, b);
+            for (int k = 2; k < (int)live.size(); ++k) {
+                const uint64_t w = nodes[(size_t)live[(size_t)k]].w;
+                if (w < nodes[(size_t)live[(size_t)a]].w) { b = a; a = k; }
+                else if (w < nodes[(size_t)live[(size_t)b]].w) b = k;
+            }
+            const int ia = live[(size_t)a], ib = live[(size_t)b];
+            nodes.push_back({nodes[(size_t)ia].w + nodes[(size_t)ib].w, ia, ib});
+            if (a > b) std::swap(a, b);
+            live.erase(live.begin() + b);
+            live.erase(live.begin() + a);
+            live.push_back((int)nodes.size() - 1);
+        }
+        int deepest = 0;
+        std::vector<std::pair<int, int>> stack{{live[0], 0}};
+        while (!stack.empty()) {
+            const auto [id, d] = stack.back();
+            stack.pop_back();
+            const Node& nd = nodes[(size_t)id];
+            if (nd.r < 0) {                           // leaf: l = -1 - symbol
+                len[-1 - nd.l] = (unsigned char)(d > 255 ? 255 : d);
+                deepest = d > deepest ? d : deepest;
+            } else {
+                stack.push_back({nd.l, d + 1});
+                stack.push_back({nd.r, d + 1});
+            }
+        }
+        if (deepest <= max_len) return;
+        for (auto& x : f)
+            if (x > 0) x = (x >> 1) > 0 ? (x >> 1) : 1;
+    }
+}
+
+// canonical codes of RFC 1951 section 3.2.2, bit-reversed (deflate packs Huffman codes most significant bit first)
+void huff_codes(const unsigned char* len, int n, uint32_t* code) {
+    int bl_count[16] = {0};
+    for (int i = 0; i < n; ++i) bl_count[len[i]]++;
+    bl_count[0] = 0;
+    uint32_t next[16] = {0}, c = 0;
+    for (int b = 1; b < 16; ++b) {
+        c = (c + (uint32_t)bl_count[b - 1]) << 1;
+        next[b] = c;
+    }
+    for (int i = 0; i < n; ++i) {
+        code[i] = 0;
+        if (len[i] == 0) continue;
+        uint32_t v = next[len[i]]++, r = 0;
+        for (int b = 0; b < len[i]; ++b) { r = (r << 1) | (v & 1u); v >>= 1; }
+        code[i] = r;
+    }
+}
+
+bool huffman_member(const char* text, size_t n_text, std::string& out) {
+    const unsigned char* in = reinterpret_cast<const unsigned char*>(text);
+    // byte histogram in four lanes (consecutive equal bytes would otherwise serialise on one counter)
+    uint64_t freq[257] = {0};
+    {
+        uint32_t h[4][256];
+        memset(h, 0, sizeof(h));
+        size_t i = 0;
+        for (; i + 4 <= n_text; i += 4) { h[0][in[i]]++; h[1][in[i + 1]]++; h[2][in[i + 2]]++; h[3][in[i + 3]]++; }
+        for (; i < n_text; ++i) h[0][in[i]]++;
+        for (int c = 0; c < 256; ++c) freq[c] = (uint64_t)h[0][c] + h[1][c] + h[2][c] + h[3][c];
+    }
+    freq[256] = 1;                                     // end of block
+    unsigned char llen[258];
+    uint32_t lcode[257];
+    huff_lengths(freq, 257, 15, llen);
+    huff_codes(llen, 257, lcode);
+    llen[257] = 0;                                     // the one distance code: zero bits = no distances used
+    // the 258 code lengths are sent one by one with the code-length code (no run-length symbols: < 150 bytes per member)
+    uint64_t cfreq[19] = {0};
+    for (int i = 0; i < 258; ++i) cfreq[llen[i]]++;
+    unsigned char clen[19];
+    uint32_t ccode[19];
+    huff_lengths(cfreq, 19, 7, clen);
+    huff_codes(clen, 19, ccode);
+    size_t bits = 0;
+    for (int c = 0; c < 257; ++c) bits += freq[c] * llen[c];
+    out.resize(10 + 64 + 19 * 3 / 8 + 258 + (bits + 7) / 8 + 8 + 16);
+    unsigned char* o = reinterpret_cast<unsigned char*>(&out[0]);
+    static const unsigned char gz_head[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
+    memcpy(o, gz_head, 10);
+    BitSink bs{o + 10};
+    bs.put(1u, 1);                                     // BFINAL
+    bs.put(2u, 2);                                     // BTYPE = dynamic Huffman
+    bs.put(0u, 5);                                     // HLIT: 257 literal / length codes
+    bs.put(0u, 5);                                     // HDIST: 1 distance code
+    bs.put(15u, 4);                                    // HCLEN: all 19 code-length codes
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (int k = 0; k < 19; ++k) bs.put(clen[order[k]], 3);
+    for (int i = 0; i < 258; ++i) bs.put(ccode[llen[i]], clen[llen[i]]);
+    // the text: code and length of a byte in one table entry
+    uint32_t tab[256];
+    for (int c = 0; c < 256; ++c) tab[c] = (lcode[c] << 4) | llen[c];
+    {
+        // two bytes per drain check: the buffer holds fewer than 32 bits before and at most 30 more after
+        unsigned char* p = bs.p;
+        uint64_t buf = bs.buf;
+        int n = bs.n;
+        size_t i = 0;
+        for (; i + 2 <= n_text; i += 2) {
+            const uint32_t e0 = tab[in[i]], e1 = tab[in[i + 1]];
+            buf |= (uint64_t)(e0 >> 4) << n;
+            n += (int)(e0 & 15u);
+            buf |= (uint64_t)(e1 >> 4) << n;
+            n += (int)(e1 & 15u);
+            if (n >= 32) {
+                memcpy(p, &buf, 4);
+                p += 4;
+                buf >>= 32;
+                n -= 32;
+            }
+        }
+        bs.p = p;
+        bs.buf = buf;
+        bs.n = n;
+        for (; i < n_text; ++i) {
+            const uint32_t e = tab[in[i]];
+            bs.put(e >> 4, (int)(e & 15u));
+        }
+    }
+    bs.put(lcode[256], llen[256]);
+    unsigned char* end = bs.finish();
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)n_text), isize = (uint32_t)n_text;
+    memcpy(end, &crc, 4);
+    memcpy(end + 4, &isize, 4);
+    out.resize((size_t)(end + 8 - o));
+    return true;
+}
+
+bool deflate_member(const char* text, size_t n_text, int level, std::string& out) {
+    if (level == 1 && n_text < ((size_t)1 << 31)) return huffman_member(text, n_text, out);
+    return zlib_member(text, n_text, level, out);
+}
+
 }  // namespace
+
+extern "C" int scdrs_gzip_member(const char* text, int64_t n_text, int32_t level, uint8_t* out, int64_t cap,
+                                 int64_t* out_len) {
+    SCDRS_CHECK(n_text >= 0 && (n_text == 0 || text) && out && out_len, "null pointer");
+    std::string gz;
+    SCDRS_CHECK(deflate_member(text ? text : "", (size_t)n_text, level, gz), "deflate failed");
+    SCDRS_CHECK((int64_t)gz.size() <= cap, "output buffer too small (%zu bytes needed)", gz.size());
+    memcpy(out, gz.data(), gz.size());
+    *out_len = (int64_t)gz.size();
+    return 0;
+}
 
 extern "C" int scdrs_format_f32(float v, char* out64) {
     char* e = fmt_f32(out64, v);

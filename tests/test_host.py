@@ -595,3 +595,30 @@ def test_save_intermediate_dumps_match_the_reference_files(tmp_path):
         got = np.loadtxt("%s.%s.tsv.gz" % (prefix, key), delimiter="\t")
         assert got.shape == gold[key].shape, key
         assert np.allclose(got, gold[key], rtol=1e-6, atol=1e-7), key
+
+
+def test_huffman_gzip_members_round_trip_and_beat_zlib_level_1(native_lib):
+    """The score-file writer's level-1 encoder (one literal-only dynamic-Huffman deflate block per gzip member,
+    csrc/score_writer.cu) against the gzip module: empty input, one byte, one repeated byte, every byte value with a
+    Fibonacci-skewed histogram (forces the length limit of 15 bits), random bytes, and score-file text -- where it
+    must not be larger than zlib at level 1."""
+    import gzip
+    import zlib
+
+    rng = np.random.default_rng(5)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    skew = b"".join(bytes([i]) * min(fib[i % 40], 200000) for i in range(256))
+    vals = rng.standard_normal(200000).astype(np.float32)
+    text = ("\t".join(_native.format_f32(v) for v in vals[:50000]) + "\n").encode()
+    cases = [b"", b"x", b"a" * 100000, skew, rng.integers(0, 256, 300000, dtype=np.uint8).tobytes(), text,
+             bytes(rng.integers(48, 58, 1 << 20, dtype=np.uint8))]
+    for data in cases:
+        gz = _native.gzip_member(data, level=1)
+        assert gzip.decompress(gz) == data
+        assert gzip.decompress(gz + gz) == data + data                 # members concatenate
+        assert gzip.decompress(_native.gzip_member(data, level=6)) == data
+    mine = len(_native.gzip_member(text, level=1))
+    ref = zlib.compressobj(1, zlib.DEFLATED, 31)
+    assert mine <= len(ref.compress(text) + ref.flush())
