@@ -74,32 +74,69 @@ gene_accum_kernel(int64_t n_cell, int n_gene, int k, int n_acc, int gpt, int n_t
                 e_l = row_lower_bound(indices, s_l, p1, my_hi);
             }
             const int nr = (int)((r1 - base) < 32 ? (r1 - base) : 32);
+            // The first 32 entries of row l + 1's segment (usually all of it) are loaded while row l is accumulated:
+            // a warp is one dependent chain load -> shared-memory read-modify-write per row, and with 16 warps per SM
+            // the load latency would otherwise be most of the kernel.
+            int64_t s = __shfl_sync(0xffffffffu, s_l, 0), e = __shfl_sync(0xffffffffu, e_l, 0);
+            int g_cur = 0;
+            float x_cur = 0.f;
+            if (s + lane < e) { g_cur = __ldg(indices + s + lane); x_cur = __ldg(data + s + lane); }
             for (int l = 0; l < nr; ++l) {
-                const int64_t s = __shfl_sync(0xffffffffu, s_l, l), e = __shfl_sync(0xffffffffu, e_l, l);
+                int64_t s_n = 0, e_n = 0;
+                int g_nxt = 0;
+                float x_nxt = 0.f;
+                if (l + 1 < nr) {
+                    s_n = __shfl_sync(0xffffffffu, s_l, l + 1);
+                    e_n = __shfl_sync(0xffffffffu, e_l, l + 1);
+                    if (s_n + lane < e_n) { g_nxt = __ldg(indices + s_n + lane); x_nxt = __ldg(data + s_n + lane); }
+                }
                 const int64_t row = base + l;
                 const double w = cell_w != nullptr ? cell_w[row] : 1.0;
+                // the row's first covariates, once per row (MODE 0); the accumulators of one entry are distinct words,
+                // so they are all read before any is written: six independent read-modify-writes instead of a chain
+                // the compiler has to keep in order (it cannot know that a[0] and a[gpt] differ)
+                double cv[4] = {0.0, 0.0, 0.0, 0.0};
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < k) cv[j] = cov_mat[row * k + j];
+                }
                 for (int64_t q = s + lane; q < e; q += 32) {
-                    const int g = __ldg(indices + q);
-                    const double x = (double)__ldg(data + q);
+                    const bool first = q < s + 32;
+                    const int g = first ? g_cur : __ldg(indices + q);
+                    const double x = (double)(first ? x_cur : __ldg(data + q));
                     double* a = ga_acc + (g - g0);
                     if (MODE == 0) {
                         const double wx = w * x;
-                        a[0] += wx;
-                        a[gpt] += wx * x;
-                        for (int j = 0; j < k; ++j) a[(size_t)(2 + j) * gpt] += wx * cov_mat[row * k + j];
+                        const double v0 = a[0], v1 = a[gpt];
+                        double t[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) t[j] = j < k ? a[(size_t)(2 + j) * gpt] : 0.0;
+                        a[0] = v0 + wx;
+                        a[gpt] = v1 + wx * x;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < k) a[(size_t)(2 + j) * gpt] = t[j] + wx * cv[j];
+                        for (int j = 4; j < k; ++j) a[(size_t)(2 + j) * gpt] += wx * cov_mat[row * k + j];
                     } else if (MODE == 1) {
                         const double t = expm1(x);
-                        a[0] += w * t;
-                        a[gpt] += w * t * t;
+                        const double v0 = a[0], v1 = a[gpt];
+                        a[0] = v0 + w * t;
+                        a[gpt] = v1 + w * t * t;
                     } else {
                         double b = gene_mean[g];
                         for (int j = 0; j < k; ++j) b = fma(cov_mat[row * k + j], cov_beta[(size_t)g * k + j], b);
                         const double kg = shift[g];
                         const double t1 = expm1(b + x) - kg, t0 = expm1(b) - kg;
-                        a[0] += w * (t1 - t0);
-                        a[gpt] += w * (t1 * t1 - t0 * t0);
+                        const double v0 = a[0], v1 = a[gpt];
+                        a[0] = v0 + w * (t1 - t0);
+                        a[gpt] = v1 + w * (t1 * t1 - t0 * t0);
                     }
                 }
+                s = s_n;
+                e = e_n;
+                g_cur = g_nxt;
+                x_cur = x_nxt;
             }
         }
     }
